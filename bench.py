@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- decode tokens/s of a synthetic Llama-3-8B "v8-k65536-256" VPTQ stack on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One step = one decode token (batch 1) through every VPTQ-quantized linear of Llama-3-8B:
+32 layers x (q 4096x4096, k/v 1024x4096, o 4096x4096, gate/up 14336x4096, down 4096x14336),
+vector_len 8, 65536 centroids + 256 residual centroids (b = 24 index bits per 8 weights),
+perm + norm enabled -- 224 fused GEMV launches chained by true data dependence
+(h -> q,k,v ; q -> o ; o -> gate,up ; gate -> down -> next layer).  Attention, norms, the
+fp16 embedding and lm_head are NOT on the VPTQ path and are not executed (stated in `config`).
+Weights are synthetic (uniform random packed indices, random codebooks); 2.6 GB of indices per
+token stream from HBM every step, ~20x the L2.
+
+Printed JSON (one line, rank 0): the driver contract + `roofline`, `cpu_baseline`, `e2e`, `clocks`.
+  value     tokens/s, inputs resident in HBM, one CUDA graph of the 224 launches per step
+  e2e       tokens/s through the C ABI with HOST buffers: pinned x -> H2D -> 224 GEMVs -> D2H -> sync
+  roofline  HBM: algorithmic bytes (packed indices + x + y of every launch) / step time
+  N > 1     tensor-parallel over out_features (one NCCL all-reduce per linear), strong scaling
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LLAMA3_8B = dict(name="llama3-8b", layers=32, hidden=4096, kv=1024, ffn=14336)
+QUANT = dict(vector_len=8, num_centroids=65536, num_res_centroids=256)
+METRIC = "decode tokens/sec Llama-3-8B 2-bit (VPTQ v8-k65536-256, b=24 index bits / 8 weights), batch 1"
+
+
+def model_linears(m):
+    h, kv, f = m["hidden"], m["kv"], m["ffn"]
+    # (name, in, out, input_of)
+    return [("q", h, h), ("k", h, kv), ("v", h, kv), ("o", h, h), ("gate", h, f), ("up", h, f), ("down", f, h)]
+
+
+def algorithmic_bytes(m, q, tokens=1, world=1):
+    """packed index bytes + x bytes + y bytes per GEMV launch, summed over a step."""
+    b = (q["num_centroids"].bit_length() - 1) + max(q["num_res_centroids"].bit_length() - 1, 0)
+    tot = 0
+    for _, i, o in model_linears(m):
+        ro = (o // world + q["vector_len"] - 1) // q["vector_len"]
+        tot += ro * ((i * b + 31) // 32) * 4 + tokens * i * 2 + tokens * (o // world) * 2
+    return tot * m["layers"]
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def build_stack(m, q, device, rank, world, dtype):
+    """Random weights for this rank's out_features shard of every linear; returns layer dicts."""
+    import torch
+    from vptq_b200 import native
+    v, K, Kr = q["vector_len"], q["num_centroids"], q["num_res_centroids"]
+    ib, rb = K.bit_length() - 1, max(Kr.bit_length() - 1, 0)
+    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    stack = []
+    for li in range(m["layers"]):
+        layer = {}
+        for name, i, o in model_linears(m):
+            o_loc = o // world
+            ro, wd = o_loc // v, (i * (ib + rb) + 31) // 32
+            t = dict(
+                indices=torch.randint(-2 ** 31, 2 ** 31 - 1, (1, ro, wd), device=device, dtype=torch.int32, generator=g),
+                # std 1/sqrt(in): unit gain, so activations stay O(1) through 224 chained layers
+                centroids=(torch.randn(1, K * v, device=device, generator=g) / i ** 0.5).to(dtype),
+                res_centroids=(0.25 * torch.randn(1, Kr * v, device=device, generator=g) / i ** 0.5).to(dtype),
+                perm=torch.randperm(i, device=device, generator=g).to(torch.int32).to(torch.uint16).view(torch.int16),
+                weight_scale=(1 + 0.1 * torch.randn(i, device=device, generator=g)).to(dtype),
+                weight_bias=(0.01 * torch.randn(i, device=device, generator=g) / i ** 0.5).to(dtype))
+            t["desc"] = native.make_desc(
+                dtype=dtype, in_features=i, out_features=o_loc, vector_len=v, num_centroids=K, num_res_centroids=Kr,
+                num_codebooks=1, group_size=i, outlier_size=0, outlier_vector_len=-1, num_outlier_centroids=-1,
+                indices=t["indices"], centroids=t["centroids"], res_centroids=t["res_centroids"], outlier_indices=None,
+                outlier_centroids=None, perm=t["perm"], weight_scale=t["weight_scale"], weight_bias=t["weight_bias"],
+                bias=None)
+            t["in"], t["out"], t["out_loc"] = i, o, o_loc
+            layer[name] = t
+        stack.append(layer)
+    return stack
+
+
+def make_step(m, stack, device, dtype, rank, world, flags):
+    """Returns (x_in, h_out, fn) where fn() enqueues one decode token on the current stream."""
+    import torch
+    import torch.distributed as dist
+    from vptq_b200 import native
+    h, kv, f = m["hidden"], m["kv"], m["ffn"]
+    buf = {n: torch.zeros(1, o, device=device, dtype=dtype) for n, o in
+           (("q", h), ("k", kv), ("v", kv), ("o", h), ("gate", f), ("up", f))}
+    hs = [torch.zeros(1, h, device=device, dtype=dtype) for _ in range(2)]
+    launches = [0]
+
+    def linear(t, x, y):
+        if world == 1:
+            native.quant_gemv(t["desc"], x, y, flags=flags)
+        else:
+            # this rank owns rows [rank*o_loc, (rank+1)*o_loc); y is full width and zero elsewhere,
+            # one all-reduce(sum) over NVLink per layer completes it (north_star)
+            y.zero_()
+            ys = y[:, rank * t["out_loc"]:(rank + 1) * t["out_loc"]]
+            native.quant_gemv(t["desc"], x, ys, flags=0)
+            dist.all_reduce(y)
+        launches[0] += 1
+
+    def step():
+        launches[0] = 0
+        cur = 0
+        for layer in stack:
+            x = hs[cur]
+            linear(layer["q"], x, buf["q"])
+            linear(layer["k"], x, buf["k"])
+            linear(layer["v"], x, buf["v"])
+            linear(layer["o"], buf["q"], buf["o"])
+            linear(layer["gate"], buf["o"], buf["gate"])
+            linear(layer["up"], buf["o"], buf["up"])
+            linear(layer["down"], buf["gate"], hs[1 - cur])
+            cur = 1 - cur
+        return hs[cur]
+
+    return hs[0], step, launches
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from vptq_b200 import native
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    native.lib()
+    dtype = torch.float16
+    m, q = LLAMA3_8B, QUANT
+    flags = 0 if args.no_pdl else native.FLAG_PDL
+
+    stack = build_stack(m, q, device, rank, world, dtype)
+    x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags)
+    x_host = torch.randn(1, m["hidden"]).to(dtype).pin_memory()
+    y_host = torch.empty(1, m["hidden"], dtype=dtype).pin_memory()
+
+    s = torch.cuda.Stream(device)
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        x_in.copy_(x_host, non_blocking=True)
+        for _ in range(2):                      # eager warm-up: smem attributes, workspace, NCCL channels
+            h_out = step()
+        s.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=s):
+            h_out = step()
+        n_launch = launches[0]
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- `value`: device-resident, W warm-up + K timed graph replays -------------------------
+        for _ in range(max(args.warmup, 3)):
+            graph.replay()
+        barrier()
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        barrier()
+        ev[0].record(s)
+        for _ in range(args.steps):
+            graph.replay()
+        ev[1].record(s)
+        barrier()
+        ms = ev[0].elapsed_time(ev[1])
+        clk = clocks.stop() if rank == 0 else None
+        assert torch.isfinite(h_out.float()).all(), "activations overflowed"
+
+        # ---- `e2e`: host buffers, H2D + D2H inside the timed region, per-step sync ------------------
+        e2e_steps = args.steps
+        for _ in range(3):
+            x_in.copy_(x_host, non_blocking=True); graph.replay(); y_host.copy_(h_out, non_blocking=True); s.synchronize()
+        barrier()
+        ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        t0 = time.perf_counter()
+        ev2[0].record(s)
+        for _ in range(e2e_steps):
+            x_in.copy_(x_host, non_blocking=True)
+            graph.replay()
+            y_host.copy_(h_out, non_blocking=True)
+            s.synchronize()
+        ev2[1].record(s)
+        barrier()
+        ms_e2e = ev2[0].elapsed_time(ev2[1])
+        wall_e2e = (time.perf_counter() - t0) * 1e3
+
+    if world > 1:
+        tms = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = tms.tolist()
+
+    if rank == 0:
+        ms_step = ms / args.steps
+        value = 1e3 / ms_step
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        abytes = algorithmic_bytes(m, q, 1, world)         # per rank and step
+        achieved = abytes / (ms_step * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "gemv_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": {"workload": "BASELINE.json configs[1]: Llama-3-8B decode batch=1 seq=1, all 224 VPTQ linears "
+                                   "(32 layers x q,k,v,o,gate,up,down), v=8 K=65536 Kr=256 (b=24), perm+norm on; "
+                                   "attention/norm/lm_head not on the VPTQ path and not executed",
+                       "parallelism": f"tp{world} (out_features sharded, 1 NCCL all-reduce per linear)" if world > 1 else "single GPU",
+                       "l2_policy": "inputs larger than L2: 2.6 GB of distinct packed indices streamed per step",
+                       "launch": "one CUDA graph per token, PDL " + ("off" if args.no_pdl else "on")},
+            "gpu_launches": n_launch * args.steps,
+            "e2e": {"value": round(1e3 / (ms_e2e / e2e_steps), 2), "unit": "tokens/s",
+                    "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2,
+                    "wall_ms_per_step": round(wall_e2e / e2e_steps, 4)},
+            "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "kernel": "gemv_kernel<half,8,1,false,true>",
+                         "algorithmic_bytes_per_launch": abytes // n_launch,
+                         "avg_launch_us": round(ms_step * 1e3 / n_launch, 3),
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
+            "clocks": clk,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(m, q, budget_s=args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference's pure-torch path (ported, see oracle/torch_port.py) on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_baseline(m, q, budget_s=20.0, min_reps=2):
+    """Bounded sample: the q_proj-shaped linear (4096x4096, b=24) of the same workload, batch 1."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port as tp
+    h = m["hidden"]
+    L = tp.synthetic_layer(h, h, q["vector_len"], q["num_centroids"], q["num_res_centroids"], seed=0)
+    x = torch.randn(1, h).to(torch.float16)
+    tp.quant_gemm(x, L)                                   # warm-up
+    times, t_start = [], time.perf_counter()
+    while len(times) < min_reps or (time.perf_counter() - t_start < budget_s and len(times) < 50):
+        t0 = time.perf_counter()
+        tp.quant_gemm(x, L)
+        times.append(time.perf_counter() - t0)
+    t = statistics.median(times)
+    fields_sample = (h // q["vector_len"]) * h
+    fields_token = sum((o // q["vector_len"]) * i for _, i, o in model_linears(m)) * m["layers"]
+    tok_s = 1.0 / (t * fields_token / fields_sample)
+    return {"value": round(tok_s, 5), "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
+            "host_cpus": os.cpu_count(),
+            "sample": f"one 4096x4096 v8-k65536-256 linear (1/{fields_token / fields_sample:.1f} of a token's index "
+                      f"fields), median of {len(times)} calls of {t * 1e3:.0f} ms, scaled to a full token; "
+                      "oracle/torch_port.py = reference torch fallback (unpack + gather + F.linear) in fp32"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    m, q = LLAMA3_8B, QUANT
+    steps = max(args.steps, 1)
+    per_step_budget = min(20.0, 150.0 / (steps + max(args.warmup, 1)))
+    cb = None
+    vals = []
+    for i in range(max(args.warmup, 1) + steps):
+        cb = cpu_baseline(m, q, budget_s=per_step_budget * 0.8, min_reps=1)
+        if i >= max(args.warmup, 1):
+            vals.append(cb["value"])
+    v = statistics.median(vals)
+    cb["value"] = v
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": max(args.warmup, 1), "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE.json configs[1] (same as --impl ours); each step = a bounded sample "
+                               "(one 4096x4096 linear) scaled to a whole token"},
+        "cpu_baseline": cb,
+        "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-pdl", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,183 @@
+/*
+ * vptq_b200.h  --  C ABI of libvptq_b200.so: the B200 (sm_100a) VPTQ quantized-linear hot path.
+ *
+ * This is the drop-in boundary.  It replaces the three pybind11 entry points the reference
+ * registers in csrc/ops.cc:44-55 (module `vptq.libvptq`, bound by vptq/ops/quant_gemm.py:22-26):
+ *
+ *   reference (pybind11, torch::Tensor in / out)          this library (plain pointers, sizes)
+ *   ---------------------------------------------------   -----------------------------------------
+ *   quant_gemv   = vptq::wquant_act16_gemv                 vptq_b200_quant_gemv
+ *                  csrc/ops.cc:20-30,49  quant_gemv.cu:241
+ *   dequant      = vptq::dequant                           vptq_b200_dequant
+ *                  csrc/ops.cc:9-18,47   dequant.cu:227
+ *   dequant + torch F.linear (vptq/ops/quant_gemm.py:231-275)
+ *                                                          vptq_b200_quant_gemm   (fused, tcgen05)
+ *   quant_gemv_v2 = vptq::quant_gemv_v2                    vptq_b200_quant_gemv_v2
+ *                  csrc/ops.cc:32-38,53  quant_gemv_v2.cu:25
+ *
+ * Conventions (differences from the reference boundary are deliberate):
+ *   - No torch types.  All tensors are raw DEVICE pointers described by vptq_linear_desc.
+ *   - The CALLER allocates outputs and workspace (the reference allocates with at::empty inside:
+ *     quant_gemv.cu:203-206, dequant.cu:186).  The library never allocates or frees device
+ *     memory, never synchronises, and only enqueues work on `stream` (a cudaStream_t passed as
+ *     void*; NULL = legacy default stream).  Every call is CUDA-graph capturable.
+ *   - Errors: return 0 on success, a negative vptq_status otherwise; vptq_b200_last_error()
+ *     returns a thread-local message (the reference throws through TORCH_CHECK,
+ *     quant_gemv.cu:252-282).  There is no CPU fallback and no silent fallback of any kind:
+ *     unsupported configurations return VPTQ_ERR_UNSUPPORTED.
+ *   - `perm` has the reference's meaning: perm[c] = original input feature of quantised column c
+ *     (csrc/kernels/quant_gemv.cuh:53-54).  The reference passes perm to quant_gemv and
+ *     argsort(perm) to dequant (vptq/ops/quant_gemm.py:208-211,222,239); here both entry points
+ *     take `perm` and derive what they need on the device.
+ *   - The workspace must be zero-filled ONCE by the caller before its first use (cudaMemset /
+ *     torch.zeros).  Kernels leave it zeroed again on completion, so it can be reused by every
+ *     subsequent call on the same stream without clearing.
+ */
+#ifndef VPTQ_B200_H_
+#define VPTQ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VPTQ_B200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define VPTQ_B200_API __attribute__((visibility("default")))
+#else
+#define VPTQ_B200_API
+#endif
+
+typedef enum vptq_dtype {
+  VPTQ_FP16 = 0, /* IEEE binary16 (torch.float16) */
+  VPTQ_BF16 = 1  /* bfloat16 (torch.bfloat16)     */
+} vptq_dtype;
+
+typedef enum vptq_status {
+  VPTQ_OK = 0,
+  VPTQ_ERR_INVALID = -1,     /* NULL / misaligned pointer, inconsistent sizes              */
+  VPTQ_ERR_UNSUPPORTED = -2, /* well-formed but not implemented (message says what)        */
+  VPTQ_ERR_WORKSPACE = -3,   /* workspace smaller than vptq_b200_workspace_bytes()         */
+  VPTQ_ERR_CUDA = -4,        /* a CUDA runtime call failed (message carries the CUDA text) */
+  VPTQ_ERR_DEVICE = -5       /* current device is not compute capability 10.x              */
+} vptq_status;
+
+/* launch flags (bit-or) */
+#define VPTQ_FLAG_PDL 1u /* launch with programmatic dependent launch: the kernel prefetches
+                            weights/codebooks/indices before griddepcontrol.wait and only then
+                            reads x; legal whenever x is produced by the preceding kernel on
+                            the same stream */
+
+/*
+ * One VQuantLinear layer: exactly the tensors the reference module owns
+ * (vptq/layers/vqlinear.py:89-240) in their checkpoint layout.  16-bit float tensors are
+ * `dtype`; index tensors are the reference's uint16-viewed-as-int16 / packed int32 words.
+ */
+typedef struct vptq_linear_desc {
+  uint32_t struct_size; /* = sizeof(vptq_linear_desc); guards ABI drift */
+  int32_t dtype;        /* vptq_dtype of x, y, centroids, scale, bias  */
+
+  int32_t in_features;           /* I                                                        */
+  int32_t out_features;          /* O                                                        */
+  int32_t vector_len;            /* v   = vector_lens[1]   (even, 2..16)                     */
+  int32_t num_centroids;         /* K   = num_centroids[1] (power of two, <= 65536)          */
+  int32_t num_res_centroids;     /* Kr  (power of two; <= 0: no residual codebook)           */
+  int32_t num_codebooks;         /* G   = group_num                                          */
+  int32_t group_size;            /* gs  columns per codebook group; S + G*gs == I            */
+  int32_t outlier_size;          /* S   leading outlier columns (0: none)                    */
+  int32_t outlier_vector_len;    /* vol = vector_lens[0]                                     */
+  int32_t num_outlier_centroids; /* Kol = num_centroids[0]                                   */
+
+  /* packed indices, int32 words [G][Ro][Wd], Ro = ceil(O/v), Wd = ceil(gs*(ib+rb)/32);
+     field j of a row = bits [j*b, (j+1)*b) of its little-endian bit stream,
+     field = idx | ridx << ib   (vptq/utils/pack.py:41-67).  Strides in 32-bit words. */
+  const int32_t* indices;
+  int64_t index_stride_codebook;
+  int64_t index_stride_row;
+
+  const void* centroids;     /* [G][K][v]   */
+  int64_t centroid_stride;   /* elements between codebooks (>= K*v) */
+  const void* res_centroids; /* [G][Kr][v]  or NULL */
+  int64_t res_centroid_stride;
+
+  const uint16_t* outlier_indices; /* [ceil(O/vol)][S] or NULL */
+  const void* outlier_centroids;   /* [Kol][vol] or NULL       */
+
+  const uint16_t* perm;     /* [I] or NULL (identity) */
+  const void* weight_scale; /* [I] or NULL; scale and bias are both present or both NULL */
+  const void* weight_bias;  /* [I] or NULL */
+  const void* bias;         /* [O] or NULL */
+} vptq_linear_desc;
+
+typedef enum vptq_op {
+  VPTQ_OP_GEMV = 0,    /* vptq_b200_quant_gemv    */
+  VPTQ_OP_DEQUANT = 1, /* vptq_b200_dequant       */
+  VPTQ_OP_GEMM = 2,    /* vptq_b200_quant_gemm    */
+  VPTQ_OP_GEMV_V2 = 3  /* vptq_b200_quant_gemv_v2 */
+} vptq_op;
+
+/* Library / device probing.  No GPU work. */
+VPTQ_B200_API int vptq_b200_abi_version(void);
+VPTQ_B200_API const char* vptq_b200_last_error(void);
+/* Bytes of zero-initialised device workspace `op` needs for this layer and token count. */
+VPTQ_B200_API size_t vptq_b200_workspace_bytes(const vptq_linear_desc* desc, int32_t tokens, int32_t op);
+
+/*
+ * Decode path: y[t][o] = sum_f x[t][f] * W[o][f] + bias[o], W never materialised.
+ * Replaces vptq::wquant_act16_gemv (csrc/quant_gemv.cu:241-294) + its `sum(-1)` epilogue
+ * (:235).  x: [tokens][x_stride] elements, y: [tokens][y_stride] elements (strides >= I / O).
+ * Any tokens >= 1 is accepted (processed in passes of <= 4); the reference routes
+ * tokens < 3 here (vptq/ops/quant_gemm.py:213).
+ */
+VPTQ_B200_API int vptq_b200_quant_gemv(const vptq_linear_desc* desc, const void* x, int64_t x_stride, void* y,
+                         int64_t y_stride, int32_t tokens, void* workspace,
+                         size_t workspace_bytes, uint32_t flags, void* stream);
+
+/*
+ * W[o][f] (row-major [O][I], `dtype`), scale/bias/perm applied -- what the reference's dequant
+ * returns (csrc/dequant.cu:227-287, Return_OUF_x_INF=true; python spec
+ * vptq/ops/quant_gemm.py:43-158).
+ */
+VPTQ_B200_API int vptq_b200_dequant(const vptq_linear_desc* desc, void* w_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/*
+ * Prefill path: y = x W^T + bias for many tokens; weight tiles are dequantised on chip and fed
+ * to tcgen05 tensor-core MMAs (replaces dequant + torch F.linear,
+ * vptq/ops/quant_gemm.py:231-275).
+ */
+VPTQ_B200_API int vptq_b200_quant_gemm(const vptq_linear_desc* desc, const void* x, int64_t x_stride, void* y,
+                         int64_t y_stride, int32_t tokens, void* workspace,
+                         size_t workspace_bytes, uint32_t flags, void* stream);
+
+/*
+ * The reference's second GEMV op with UNPACKED indices (csrc/quant_gemv_v2.cu:25-180; layout
+ * pinned by tests/test_quant_gemv.py:86-105): indices u16 [Ro][I], residual_indices u8
+ * (res_index_bytes == 1) or u16 (== 2) [Ro][I] or NULL, scale_weights/scale_bias [I] or NULL,
+ * one codebook, no perm, no outliers.
+ */
+VPTQ_B200_API int vptq_b200_quant_gemv_v2(int32_t dtype, const void* x, void* y, int32_t tokens,
+                            int32_t in_features, int32_t out_features, int32_t vector_len,
+                            int32_t num_centroids, int32_t num_res_centroids,
+                            const uint16_t* indices, const void* centroids,
+                            const void* residual_indices, int32_t res_index_bytes,
+                            const void* residual_centroids, const void* scale_weights,
+                            const void* scale_bias, const void* bias, void* workspace,
+                            size_t workspace_bytes, uint32_t flags, void* stream);
+
+/*
+ * End-to-end helper used by the `e2e` measurement: x_host -> (H2D) -> GEMV/GEMM -> (D2H) ->
+ * y_host on `stream`, then a stream synchronise.  x_dev / y_dev are caller-provided device
+ * staging buffers ([tokens][I] / [tokens][O]); host buffers should be pinned.
+ */
+VPTQ_B200_API int vptq_b200_linear_host(const vptq_linear_desc* desc, const void* x_host, void* y_host,
+                          int32_t tokens, void* x_dev, void* y_dev, void* workspace,
+                          size_t workspace_bytes, uint32_t flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VPTQ_B200_H_ */

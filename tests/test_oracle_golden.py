@@ -106,3 +106,25 @@ def test_gemv_v2_layout_matches_reference_test_loop():
     want = vo.bf16_bits_to_f32(x).reshape(1, I).astype(np.float64) @ W
     got = vo.quant_gemv_v2(x, None, idx, C, ridx, R, sw, sb, v, O, dtype="bf16")
     np.testing.assert_allclose(got.reshape(1, O), want, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_torch_port_matches_reference(name):
+    """oracle/torch_port.py (the multi-threaded CPU baseline bench.py times) == reference python."""
+    import torch
+    import torch_port as tp
+    L, x, ref = load_golden(name)
+    f = (lambda a: None if a is None else (torch.from_numpy(np.asarray(a, dtype=np.float16).copy()) if L.dtype == "fp16"
+         else torch.from_numpy(np.asarray(a, dtype=np.uint16).copy()).view(torch.bfloat16)))
+    u = lambda a: None if a is None else torch.from_numpy(np.asarray(a, dtype=np.uint16).copy()).view(torch.int16)
+    d = dict(in_features=L.in_features, out_features=L.out_features, vector_len=L.vector_len,
+             num_centroids=L.num_centroids, num_res_centroids=L.num_res_centroids, num_codebooks=L.num_codebooks,
+             group_size=L.group_size, outlier_size=L.outlier_size if L.enable_outlier else 0,
+             outlier_vector_len=L.outlier_vector_len, num_outlier_centroids=L.num_outlier_centroids,
+             indices=torch.from_numpy(L.indices.copy()), centroids=f(L.centroids), res_centroids=f(L.res_centroids),
+             outlier_indices=u(L.outlier_indices), outlier_centroids=f(L.outlier_centroids), perm=u(L.perm),
+             weight_scale=f(L.weight_scale), weight_bias=f(L.weight_bias), bias=f(L.bias))
+    W = tp.dequant(d).numpy()
+    np.testing.assert_allclose(W, ref["W_ref"], rtol=1e-6, atol=1e-7)
+    y = tp.quant_gemm(f(x), d).numpy()
+    assert np.abs(y - ref["y_ref"]).max() <= 2e-5 * np.abs(ref["y_ref"]).max()

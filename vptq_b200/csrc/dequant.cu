@@ -1,0 +1,188 @@
+// Dequantise a VPTQ layer to a dense [out_features][in_features] 16-bit matrix in ORIGINAL column
+// order with weight_scale / weight_bias applied -- the tensor the reference's `dequant` op returns
+// (csrc/dequant.cu:227-287, kernel csrc/kernels/dequant.cuh:9-115; python spec
+// vptq/ops/quant_gemm.py:43-158).
+//
+// Thread mapping: a thread owns two adjacent ORIGINAL columns f, f+1 of one index row, so a warp
+// stores 128 contiguous bytes per output row (the reference stores one 2-byte element per thread
+// and row).  (C + R) * scale + bias is evaluated in fp32 and rounded once.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vptq_b200 {
+
+namespace {
+
+struct DequantParams {
+  const uint32_t* indices;
+  int64_t idx_stride_g, idx_stride_r;
+  const void* centroids;
+  int64_t cb_stride;
+  const void* res_centroids;
+  int64_t rcb_stride;
+  const uint16_t* outlier_idx;
+  const void* outlier_cb;
+  const uint16_t* inv_perm;  // [I] or nullptr
+  const void* scale;
+  const void* wbias;
+  void* out;
+  int I, O, Ro, G, gs, S, vol;
+  int ib, rb;
+};
+
+__global__ void invert_perm_kernel(const uint16_t* __restrict__ perm, uint16_t* __restrict__ inv, int n) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < n) inv[perm[c]] = uint16_t(c);
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256) dequant_kernel(const __grid_constant__ DequantParams p) {
+  const int r = blockIdx.y;
+  const int fbase = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (fbase >= p.I) return;
+  const T* scale = reinterpret_cast<const T*>(p.scale);
+  const T* wbias = reinterpret_cast<const T*>(p.wbias);
+  const int b = p.ib + p.rb;
+  const uint32_t fmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+  const uint64_t pol = policy_evict_last();
+
+  float val[2][V];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int f = fbase + h;
+    if (f >= p.I) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) val[h][e] = 0.f;
+      continue;
+    }
+    const int c = p.inv_perm ? int(p.inv_perm[f]) : f;
+    const float sc = scale ? DT<T>::to_float(scale[f]) : 1.f;
+    const float wb = wbias ? DT<T>::to_float(wbias[f]) : 0.f;
+    if (c < p.S) {  // outlier column: its own codebook with vector length `vol`
+      const T* ocb = reinterpret_cast<const T*>(p.outlier_cb);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const int o = r * V + e;
+        float w = 0.f;
+        if (o < p.O) {
+          const int rol = o / p.vol, eo = o - rol * p.vol;
+          const int oi = p.outlier_idx[int64_t(rol) * p.S + c];
+          w = DT<T>::to_float(ocb[int64_t(oi) * p.vol + eo]);
+        }
+        val[h][e] = fmaf(w, sc, wb);
+      }
+    } else {
+      const int ci = c - p.S;
+      const int g = ci / p.gs, j = ci - g * p.gs;
+      const uint32_t* row = p.indices + int64_t(g) * p.idx_stride_g + int64_t(r) * p.idx_stride_r;
+      const uint32_t bit = uint32_t(j) * uint32_t(b);
+      const uint32_t w0 = bit >> 5, sh = bit & 31u;
+      const uint32_t lo = ldg_nc_u32(row + w0);
+      const uint32_t hi = (sh + b > 32) ? ldg_nc_u32(row + w0 + 1) : 0u;  // never reads past the row
+      const uint32_t field = __funnelshift_r(lo, hi, sh) & fmask;
+      const uint32_t mi = field & ((1u << p.ib) - 1u), ri = field >> p.ib;
+      uint32_t cw[V / 2];
+      ldg_entry<V>(cw, reinterpret_cast<const T*>(p.centroids) + int64_t(g) * p.cb_stride + size_t(mi) * V, pol);
+      float w[V];
+#pragma unroll
+      for (int i = 0; i < V / 2; ++i) {
+        const float2 t = DT<T>::unpack2(cw[i]);
+        w[2 * i] = t.x, w[2 * i + 1] = t.y;
+      }
+      if (p.rb) {
+        uint32_t rw[V / 2];
+        ldg_entry<V>(rw, reinterpret_cast<const T*>(p.res_centroids) + int64_t(g) * p.rcb_stride + size_t(ri) * V, pol);
+#pragma unroll
+        for (int i = 0; i < V / 2; ++i) {
+          const float2 t = DT<T>::unpack2(rw[i]);
+          w[2 * i] += t.x, w[2 * i + 1] += t.y;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) val[h][e] = fmaf(w[e], sc, wb);
+    }
+  }
+
+  T* out = reinterpret_cast<T*>(p.out);
+  const bool pair = (fbase + 1 < p.I) && ((p.I & 1) == 0);
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const int o = r * V + e;
+    if (o >= p.O) break;  // padding rows are dropped (vptq/ops/quant_gemm.py:123-124)
+    T* dst = out + int64_t(o) * p.I + fbase;
+    if (pair) {
+      *reinterpret_cast<uint32_t*>(dst) = DT<T>::pack2(val[0][e], val[1][e]);
+    } else {
+      dst[0] = DT<T>::from_float(val[0][e]);
+      if (fbase + 1 < p.I) dst[1] = DT<T>::from_float(val[1][e]);
+    }
+  }
+}
+
+template <typename T>
+int launch_v(const DequantParams& p, int v, cudaStream_t stream) {
+  dim3 block(256), grid(unsigned((p.I + 511) / 512), unsigned(p.Ro));
+  switch (v) {
+#define VPTQ_CASE(VV) \
+  case VV: dequant_kernel<T, VV><<<grid, block, 0, stream>>>(p); break;
+    VPTQ_CASE(2) VPTQ_CASE(4) VPTQ_CASE(6) VPTQ_CASE(8) VPTQ_CASE(10) VPTQ_CASE(12) VPTQ_CASE(16)
+#undef VPTQ_CASE
+    default: set_error("dequant: vector_len %d not supported", v); return VPTQ_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("dequant launch: %s", cudaGetErrorString(e));
+    return VPTQ_ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // namespace
+
+size_t dequant_workspace_bytes(const vptq_linear_desc& d) {
+  return d.perm ? align_up(size_t(d.in_features) * 2, 256) : 0;
+}
+
+int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream) {
+  DequantParams p{};
+  p.indices = reinterpret_cast<const uint32_t*>(d.indices);
+  p.idx_stride_g = d.index_stride_codebook, p.idx_stride_r = d.index_stride_row;
+  p.centroids = d.centroids, p.cb_stride = d.centroid_stride;
+  p.res_centroids = d.res_centroids, p.rcb_stride = d.res_centroid_stride;
+  p.I = d.in_features, p.O = d.out_features, p.G = d.num_codebooks, p.gs = d.group_size;
+  p.Ro = (d.out_features + d.vector_len - 1) / d.vector_len;
+  p.ib = ilog2(d.num_centroids);
+  p.rb = d.num_res_centroids > 0 ? ilog2(d.num_res_centroids) : 0;
+  p.S = (d.outlier_size > 0 && d.outlier_indices) ? d.outlier_size : 0;
+  p.vol = p.S ? d.outlier_vector_len : 1;
+  p.outlier_idx = p.S ? d.outlier_indices : nullptr;
+  p.outlier_cb = p.S ? d.outlier_centroids : nullptr;
+  p.scale = d.weight_scale, p.wbias = d.weight_bias;
+  p.out = w_out;
+  p.inv_perm = nullptr;
+  if (d.perm) {
+    const size_t need = dequant_workspace_bytes(d);
+    if (!workspace || workspace_bytes < need) {
+      set_error("dequant: workspace %zu bytes < required %zu (inverse permutation)", workspace_bytes, need);
+      return VPTQ_ERR_WORKSPACE;
+    }
+    uint16_t* inv = reinterpret_cast<uint16_t*>(workspace);
+    invert_perm_kernel<<<(d.in_features + 255) / 256, 256, 0, stream>>>(d.perm, inv, d.in_features);
+    p.inv_perm = inv;
+  }
+  const int rc = d.dtype == VPTQ_FP16 ? launch_v<__half>(p, d.vector_len, stream)
+                                      : launch_v<__nv_bfloat16>(p, d.vector_len, stream);
+  if (rc) return rc;
+  if (d.perm) {
+    // the GEMV's split-K counters share this workspace and expect it zeroed at rest
+    cudaError_t e = cudaMemsetAsync(workspace, 0, dequant_workspace_bytes(d), stream);
+    if (e != cudaSuccess) {
+      set_error("dequant: workspace reset: %s", cudaGetErrorString(e));
+      return VPTQ_ERR_CUDA;
+    }
+  }
+  return 0;
+}
+
+}  // namespace vptq_b200

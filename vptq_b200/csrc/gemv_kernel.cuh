@@ -1,0 +1,358 @@
+// Fused decode GEMV for VPTQ-quantized linear layers on sm_100a.
+//
+//   y[t][o] = sum_c x'[t][c] * Wq[o][c]  +  sum_f x[t][f] * wbias[f]  +  bias[o]
+//   x'[t][c] = x[t][perm[c]] * scale[perm[c]],   Wq[r*v+e][c] = C[idx[r][c]][e] + R[ridx[r][c]][e]
+//
+// (same mathematics as the reference's WqA16WithOutliers_PackIndice,
+// csrc/kernels/quant_gemv.cuh:11-186, with the three hoists it does not make: x' is formed once
+// per CTA instead of per (row, column); the weight_bias term is a per-token scalar added in the
+// epilogue; accumulation is fp32.)  Nothing here is derived from the reference's kernel
+// structure: rows are owned by warps, the packed index words of a row arrive through a per-warp
+// ring of 1-D TMA bulk copies (cp.async.bulk + mbarrier), codebooks are staged in shared memory
+// (bank-group replicated when small) or gathered through L1/L2 with an evict_last policy, and
+// the split-K reduction is a deterministic "last CTA sums in chunk order" epilogue instead of a
+// second kernel.
+#pragma once
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vptq_b200 {
+
+struct GemvParams {
+  // layer
+  const uint32_t* indices;
+  int64_t idx_stride_g, idx_stride_r;  // 32-bit words
+  const void* centroids;
+  int64_t cb_stride;  // elements
+  const void* res_centroids;
+  int64_t rcb_stride;
+  const uint16_t* outlier_idx;
+  const void* outlier_cb;
+  const uint16_t* perm;
+  const void* scale;
+  const void* wbias;
+  const void* bias;
+  // activations
+  const void* x;
+  void* y;
+  int64_t x_stride, y_stride;  // elements per token
+  // split-K workspace
+  float* partials;
+  uint32_t* counters;
+  // shapes
+  int I, O, Ro, G, gs, S, vol, Kol, Rol;
+  int K, Kr, ib, rb;
+  int idx_tma_ok;  // rows are 16-byte aligned -> bulk copies legal
+  GemvPlan plan;
+};
+
+// accumulate x * (c + r) into acc[V] for one gathered (main, residual) entry pair
+template <typename T, int V, bool RES>
+__device__ __forceinline__ void fma_entry(float (&acc)[V], float xv, const uint32_t (&cw)[V / 2],
+                                          const uint32_t (&rw)[V / 2]) {
+#pragma unroll
+  for (int i = 0; i < V / 2; ++i) {
+    float2 c = DT<T>::unpack2(cw[i]);
+    if constexpr (RES) {
+      float2 r = DT<T>::unpack2(rw[i]);
+      c.x += r.x;
+      c.y += r.y;
+    }
+    acc[2 * i] = fmaf(xv, c.x, acc[2 * i]);
+    acc[2 * i + 1] = fmaf(xv, c.y, acc[2 * i + 1]);
+  }
+}
+
+template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
+__global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  constexpr int U = 4;              // fields per lane in flight
+  constexpr int EB = 2 * V;         // bytes per codebook entry
+  const GemvPlan& pl = p.plan;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int chunk = blockIdx.x % pl.nch;
+  const int cta_in_chunk = blockIdx.x / pl.nch;
+  const int g = chunk / pl.cpg, cig = chunk % pl.cpg;
+  const int f0 = cig * pl.chunk_cols;
+  const int f1 = min(p.gs, f0 + pl.chunk_cols);
+  const int ncols = f1 - f0;
+  const bool owns_outliers = (chunk == 0) && (p.S > 0);
+  const int n_all = ncols + (owns_outliers ? p.S : 0);
+  const int b = p.ib + p.rb;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + pl.off_bars);
+  float* s_cbias = reinterpret_cast<float*>(smem + pl.off_cbias);
+  uint16_t* s_pcol = reinterpret_cast<uint16_t*>(smem + pl.off_pcol);
+  float* s_wb = reinterpret_cast<float*>(smem + pl.off_wb);
+  float* sx = reinterpret_cast<float*>(smem + pl.off_sx);
+  uint8_t* s_res = smem + pl.off_res;
+  uint8_t* s_main = smem + pl.off_main;
+  uint8_t* ring = smem + pl.off_ring + warp * pl.stages * pl.stage_bytes;
+  uint64_t* cb_bar = &bars[0];
+  uint64_t* full = &bars[1 + warp * pl.stages];
+
+  const T* cent_g = reinterpret_cast<const T*>(p.centroids) + int64_t(g) * p.cb_stride;
+  const T* res_g = RES ? reinterpret_cast<const T*>(p.res_centroids) + int64_t(g) * p.rcb_stride : nullptr;
+
+  // -------- barrier init -----------------------------------------------------------------
+  if (tid == 0) {
+    mbar_init(cb_bar, 1);
+    for (int i = 0; i < nwarps * pl.stages; ++i) mbar_init(&bars[1 + i], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();  // the next kernel may start its own weight-only prologue now
+
+  const uint64_t pol_stream = policy_evict_first();
+  const uint64_t pol_keep = policy_evict_last();
+
+  // -------- work list of this warp -------------------------------------------------------
+  const int nrows_cta = cta_in_chunk < p.Ro ? (p.Ro - cta_in_chunk + pl.cpc - 1) / pl.cpc : 0;
+  const int nunits = warp < nrows_cta ? (nrows_cta - warp + nwarps - 1) / nwarps : 0;
+  const int nseg = (ncols + pl.seg_fields - 1) / pl.seg_fields;
+  const int total = nunits * nseg;
+  const uint32_t* idx_g = p.indices + int64_t(g) * p.idx_stride_g;
+
+  // warp-collective: start the copy of segment q of this warp's work list into its ring stage
+  auto issue = [&](int q) {
+    const int u = q / nseg, s = q - u * nseg;
+    const int r = cta_in_chunk + pl.cpc * (warp + nwarps * u);
+    const int fs = f0 + s * pl.seg_fields;
+    const int nf = min(pl.seg_fields, f1 - fs);
+    const uint32_t* src = idx_g + int64_t(r) * p.idx_stride_r + ((int64_t(fs) * b) >> 5);
+    const int nw = (nf * b + 31) >> 5;
+    const int st = q % pl.stages;
+    uint8_t* dst = ring + st * pl.stage_bytes;
+    if (p.idx_tma_ok && (nw & 3) == 0) {
+      if (lane == 0) {
+        fence_proxy_async_smem();
+        mbar_arrive_expect_tx(&full[st], uint32_t(nw) * 4u);
+        tma_bulk_g2s(dst, src, uint32_t(nw) * 4u, &full[st], pol_stream);
+      }
+    } else {  // ragged / unaligned rows: plain word copy by the whole warp
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+      for (int i = lane; i < nw; i += 32) d32[i] = ldg_nc_u32(src + i);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[st]);
+    }
+  };
+
+  // index stream: fill the ring before anything else so HBM latency overlaps the prologue
+  const int npre = min(total, pl.stages);
+  for (int q = 0; q < npre; ++q) issue(q);
+
+  // -------- codebooks -> shared memory (weights only: legal before the PDL wait) -----------
+  // rep == 1: one TMA bulk copy.  rep == 8: entry i is stored 8 times, copy k at 16-byte slot
+  // i*8+k, so that lane L reads slot i*8 + (L & 7): the 8 lanes of a quarter-warp always hit
+  // 8 different 16-byte bank groups -> conflict-free 128-bit gathers.
+  uint32_t cb_tx = 0;
+  auto stage_table = [&](uint8_t* dst, const T* src, int entries, int rep) {
+    const uint32_t bytes = uint32_t(entries) * EB;
+    if (rep == 1 && (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      if (tid == 0) {
+        for (uint32_t off = 0; off < bytes; off += 32768u) {
+          const uint32_t n = min(32768u, bytes - off);
+          tma_bulk_g2s(dst + off, reinterpret_cast<const uint8_t*>(src) + off, n, cb_bar, pol_keep);
+        }
+      }
+      cb_tx += bytes;
+    } else {
+      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
+      uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
+      constexpr int WPE = V / 2;  // words per entry
+      for (int i = tid; i < entries * WPE; i += blockDim.x) {
+        const uint32_t w = ldg_nc_u32(s32 + i);
+        const int e = i / WPE, k = i - e * WPE;
+        for (int c = 0; c < rep; ++c) d32[(e * rep + c) * WPE + k] = w;
+      }
+    }
+  };
+  if constexpr (RES) stage_table(s_res, res_g, p.Kr, pl.res_rep);
+  if constexpr (MAIN_SMEM) stage_table(s_main, cent_g, p.K, pl.main_rep);
+  if (tid == 0) {
+    if (cb_tx) mbar_arrive_expect_tx(cb_bar, cb_tx);
+    else mbar_arrive(cb_bar);
+  }
+
+  // -------- x' prologue, phase A: everything that does not depend on x --------------------
+  const T* scale = reinterpret_cast<const T*>(p.scale);
+  const T* wbias = reinterpret_cast<const T*>(p.wbias);
+  for (int i = tid; i < n_all; i += blockDim.x) {
+    const int c = i < ncols ? p.S + g * p.gs + f0 + i : i - ncols;
+    const int pc = p.perm ? int(p.perm[c]) : c;
+    s_pcol[i] = uint16_t(pc);
+    sx[i] = scale ? DT<T>::to_float(scale[pc]) : 1.f;
+    s_wb[i] = wbias ? DT<T>::to_float(wbias[pc]) : 0.f;
+  }
+
+  // -------- phase B: x arrives from the previous kernel ------------------------------------
+  pdl_wait_prior_grid();
+  {
+    const T* x = reinterpret_cast<const T*>(p.x);
+    float bs[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) bs[t] = 0.f;
+    for (int i = tid; i < n_all; i += blockDim.x) {
+      const int pc = s_pcol[i];
+      const float sc = sx[i], wb = s_wb[i];
+#pragma unroll
+      for (int t = NT - 1; t >= 0; --t) {
+        const float xv = DT<T>::to_float(x[int64_t(t) * p.x_stride + pc]);
+        sx[t * pl.sx_stride + i] = xv * sc;
+        bs[t] = fmaf(xv, wb, bs[t]);
+      }
+    }
+    // block-reduce the weight_bias term of this chunk: s_cbias[t] = sum_{c in chunk} x[perm c]*wbias[perm c]
+    float* red = s_cbias + NT;  // [NT][nwarps] scratch
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      const float v = warp_sum(bs[t]);
+      if (lane == 0) red[t * nwarps + warp] = v;
+    }
+    __syncthreads();
+    if (tid < NT) {
+      float v = 0.f;
+      for (int w = 0; w < nwarps; ++w) v += red[tid * nwarps + w];
+      s_cbias[tid] = v;
+    }
+  }
+  __syncthreads();
+  if constexpr (RES || MAIN_SMEM) mbar_wait(cb_bar, 0);
+
+  // -------- main loop ------------------------------------------------------------------------
+  const uint32_t fmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+  const uint32_t imask = (1u << p.ib) - 1u;
+  const uint32_t main_stride = uint32_t(EB) * (MAIN_SMEM ? pl.main_rep : 1);
+  const uint32_t res_stride = uint32_t(EB) * pl.res_rep;
+  const uint32_t s_main_lane = smem_u32(s_main) + (pl.main_rep > 1 ? (lane & 7) * EB : 0);
+  const uint32_t s_res_lane = smem_u32(s_res) + (pl.res_rep > 1 ? (lane & 7) * EB : 0);
+  const uint8_t* cent_bytes = reinterpret_cast<const uint8_t*>(cent_g);
+
+  float acc[NT][V];
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int e = 0; e < V; ++e) acc[t][e] = 0.f;
+
+  for (int q = 0; q < total; ++q) {
+    const int u = q / nseg, s = q - u * nseg;
+    const int r = cta_in_chunk + pl.cpc * (warp + nwarps * u);
+    const int seg0 = s * pl.seg_fields;  // first field of the segment, relative to the chunk
+    const int nf = min(pl.seg_fields, ncols - seg0);
+    const int st = q % pl.stages;
+    mbar_wait(&full[st], uint32_t(q / pl.stages) & 1u);
+    const uint32_t* sw = reinterpret_cast<const uint32_t*>(ring + st * pl.stage_bytes);
+    const float* sxs = sx + seg0;
+
+    for (int jb = 0; jb < nf; jb += 32 * U) {
+      uint32_t mi[U], ri[U];
+      float xv[U][NT];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int j = jb + 32 * k + lane;
+        const bool valid = j < nf;
+        const uint32_t bit = uint32_t(j) * uint32_t(b);
+        const uint32_t w = bit >> 5;
+        uint32_t f = __funnelshift_r(sw[w], sw[w + 1], bit & 31u) & fmask;
+        f = valid ? f : 0u;  // out-of-range lanes gather entry 0 and multiply by zero
+        mi[k] = f & imask;
+        ri[k] = f >> p.ib;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) xv[k][t] = valid ? sxs[t * pl.sx_stride + j] : 0.f;
+      }
+      uint32_t cw[U][V / 2], rw[U][V / 2];
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        if constexpr (MAIN_SMEM) lds_entry<V>(cw[k], s_main_lane + mi[k] * main_stride);
+        else ldg_entry<V>(cw[k], cent_bytes + size_t(mi[k]) * EB, pol_keep);
+        if constexpr (RES) lds_entry<V>(rw[k], s_res_lane + ri[k] * res_stride);
+      }
+#pragma unroll
+      for (int k = 0; k < U; ++k)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) fma_entry<T, V, RES>(acc[t], xv[k][t], cw[k], rw[k]);
+    }
+    __syncwarp();  // every lane's index words are in registers (its gathers depended on them)
+    if (q + pl.stages < total) issue(q + pl.stages);
+
+    if (s != nseg - 1) continue;
+
+    // ---- row finished: outlier columns (owned by chunk 0), reduction, store ---------------
+    if (owns_outliers) {
+      const T* ocb = reinterpret_cast<const T*>(p.outlier_cb);
+      const float* sxo = sx + ncols;
+      for (int c = lane; c < p.S; c += 32) {
+        float xo[NT];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) xo[t] = sxo[t * pl.sx_stride + c];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const int o = r * V + e;
+          if (o < p.O) {
+            const int rol = o / p.vol, eo = o - rol * p.vol;
+            const int oi = p.outlier_idx[int64_t(rol) * p.S + c];
+            const float w = DT<T>::to_float(ocb[int64_t(oi) * p.vol + eo]);
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[t][e] = fmaf(xo[t], w, acc[t][e]);
+          }
+        }
+      }
+    }
+    // butterfly: afterwards every lane holds the row's full sums; lane e keeps output e
+    float mine[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      mine[t] = 0.f;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float v = warp_sum(acc[t][e]);
+        if (lane == e) mine[t] = v;
+        acc[t][e] = 0.f;
+      }
+    }
+    const int o = r * V + lane;
+    const bool writer = lane < V && o < p.O;
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    T* y = reinterpret_cast<T*>(p.y);
+    if (pl.nch == 1) {
+      if (writer) {
+        const float bv = bias ? DT<T>::to_float(bias[o]) : 0.f;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(mine[t] + s_cbias[t] + bv);
+      }
+    } else {
+      const int64_t opad = int64_t(p.Ro) * V;
+      if (lane < V) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) p.partials[(int64_t(chunk) * NT + t) * opad + r * V + lane] = mine[t] + s_cbias[t];
+        __threadfence();
+      }
+      __syncwarp();
+      uint32_t prev = 0;
+      if (lane == 0) prev = atomicAdd(&p.counters[r], 1u);
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if (prev == uint32_t(pl.nch - 1)) {  // last chunk of this row to arrive: sum in chunk order
+        __threadfence();
+        if (writer) {
+          const float bv = bias ? DT<T>::to_float(bias[o]) : 0.f;
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            float v = 0.f;
+            for (int ch = 0; ch < pl.nch; ++ch) v += ldg_cg_f32(&p.partials[(int64_t(ch) * NT + t) * opad + r * V + lane]);
+            y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(v + bv);
+          }
+        }
+        if (lane == 0) p.counters[r] = 0u;  // leave the workspace zeroed for the next launch
+      }
+    }
+  }
+}
+
+using GemvKernelFn = void (*)(const GemvParams);
+// one definition per (dtype, V) translation unit, see gemv_inst_*.cu
+GemvKernelFn gemv_kernel_v8(int dtype, int nt, bool main_smem, bool res);
+GemvKernelFn gemv_kernel_vx(int dtype, int v, bool main_smem, bool res);
+
+}  // namespace vptq_b200

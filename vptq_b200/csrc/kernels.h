@@ -1,0 +1,100 @@
+// Internal interface between the C-ABI layer (api.cu) and the kernel translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/vptq_b200.h"
+
+namespace vptq_b200 {
+
+struct DeviceInfo {
+  int device = -1;
+  int sm_count = 0;
+  int cc_major = 0, cc_minor = 0;
+  int smem_optin = 0;  // max dynamic shared memory per block (opt-in), bytes
+  int l2_bytes = 0;
+};
+// cached per device; returns nullptr (and sets the error) on failure
+const DeviceInfo* device_info();
+
+void set_error(const char* fmt, ...);
+
+static inline int ilog2(int64_t v) {
+  int r = 0;
+  while ((int64_t(1) << (r + 1)) <= v) ++r;
+  return r;
+}
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// -------------------------------------------------------------------------------------------
+// decode GEMV
+// -------------------------------------------------------------------------------------------
+// How one launch is cut up.  Units of work are (index row r, column chunk); a CTA owns one
+// chunk (so its x' slice and codebooks are staged once) and a strided subset of the rows; each
+// of its warps owns whole rows, streams their packed index words through a private TMA ring and
+// keeps the v partial sums in registers.
+struct GemvPlan {
+  int threads;         // CTA size (multiple of 32)
+  int grid;            // nch * cpc
+  int nch;             // column chunks in total = G * cpg
+  int cpg;             // chunks per codebook group
+  int chunk_cols;      // columns per chunk (multiple of 128 except possibly the group's last)
+  int cpc;             // CTAs per chunk (rows are dealt round-robin to them)
+  int seg_fields;      // index fields per ring stage (multiple of 128)
+  int stages;          // ring depth per warp
+  int main_in_smem;    // main codebook staged in shared memory (else gathered through L1/L2)
+  int main_rep;        // bank-group replication factor of the main codebook in smem (1 or 8)
+  int res_rep;         // same for the residual codebook
+  int nt;              // tokens per pass (1, 2 or 4)
+  int sx_stride;       // floats per token row of x' in smem
+  uint32_t off_bars, off_cbias, off_pcol, off_wb, off_sx, off_res, off_main, off_ring;
+  uint32_t stage_bytes;
+  uint32_t smem_bytes;
+  // workspace carve-up
+  size_t ws_counters_bytes;  // Ro uint32 (zero at rest)
+  size_t ws_partials_bytes;  // nch * nt * Ro*v floats (only when nch > 1)
+};
+
+// Fills `plan` for (desc, tokens-per-pass).  Returns 0 or a vptq_status.
+int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev, GemvPlan* plan);
+// Launches ceil(tokens / plan.nt) passes.
+int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void* y, int64_t y_stride,
+                int tokens, void* workspace, size_t workspace_bytes, uint32_t flags, cudaStream_t stream);
+
+// -------------------------------------------------------------------------------------------
+// dequant
+// -------------------------------------------------------------------------------------------
+size_t dequant_workspace_bytes(const vptq_linear_desc& d);
+int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream);
+
+// -------------------------------------------------------------------------------------------
+// prefill GEMM (tcgen05)
+// -------------------------------------------------------------------------------------------
+size_t gemm_workspace_bytes(const vptq_linear_desc& d, int tokens);
+int gemm_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void* y, int64_t y_stride,
+                int tokens, void* workspace, size_t workspace_bytes, uint32_t flags, cudaStream_t stream);
+
+// -------------------------------------------------------------------------------------------
+// v2 GEMV (unpacked indices)
+// -------------------------------------------------------------------------------------------
+struct GemvV2Args {
+  int dtype, tokens, in_features, out_features, vector_len, num_centroids, num_res_centroids;
+  const void* x;
+  void* y;
+  const uint16_t* indices;
+  const void* centroids;
+  const void* residual_indices;
+  int res_index_bytes;
+  const void* residual_centroids;
+  const void* scale_weights;
+  const void* scale_bias;
+  const void* bias;
+};
+size_t gemv_v2_workspace_bytes(int tokens, int in_features, int out_features, int vector_len);
+int gemv_v2_launch(const GemvV2Args& a, void* workspace, size_t workspace_bytes, uint32_t flags,
+                   cudaStream_t stream);
+
+}  // namespace vptq_b200

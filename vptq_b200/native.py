@@ -1,0 +1,208 @@
+"""ctypes binding of libvptq_b200.so (the C ABI declared in include/vptq_b200.h).
+
+This is the only bridge between the Python surface and the CUDA kernels.  There is no other
+implementation behind it: if the shared library is missing or a call fails, a RuntimeError is
+raised -- no CPU path, no torch fallback (the reference silently falls back to a torch
+implementation when its extension is absent, vptq/ops/quant_gemm.py:20-40; this package does not).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvptq_b200.so")
+
+VPTQ_FP16, VPTQ_BF16 = 0, 1
+OP_GEMV, OP_DEQUANT, OP_GEMM, OP_GEMV_V2 = 0, 1, 2, 3
+FLAG_PDL = 1
+ABI_VERSION = 1
+
+EXPORTS = (
+    "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
+    "vptq_b200_dequant", "vptq_b200_quant_gemm", "vptq_b200_quant_gemv_v2", "vptq_b200_linear_host",
+)
+
+
+class LinearDesc(ctypes.Structure):
+    """struct vptq_linear_desc (include/vptq_b200.h)."""
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32), ("dtype", ctypes.c_int32),
+        ("in_features", ctypes.c_int32), ("out_features", ctypes.c_int32),
+        ("vector_len", ctypes.c_int32), ("num_centroids", ctypes.c_int32),
+        ("num_res_centroids", ctypes.c_int32), ("num_codebooks", ctypes.c_int32),
+        ("group_size", ctypes.c_int32), ("outlier_size", ctypes.c_int32),
+        ("outlier_vector_len", ctypes.c_int32), ("num_outlier_centroids", ctypes.c_int32),
+        ("indices", ctypes.c_void_p), ("index_stride_codebook", ctypes.c_int64),
+        ("index_stride_row", ctypes.c_int64),
+        ("centroids", ctypes.c_void_p), ("centroid_stride", ctypes.c_int64),
+        ("res_centroids", ctypes.c_void_p), ("res_centroid_stride", ctypes.c_int64),
+        ("outlier_indices", ctypes.c_void_p), ("outlier_centroids", ctypes.c_void_p),
+        ("perm", ctypes.c_void_p), ("weight_scale", ctypes.c_void_p), ("weight_bias", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p),
+    ]
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> ctypes.CDLL:
+    """Load the shared library (once).  Fails loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m vptq_b200.build` "
+                "(vptq_b200 has no CPU or torch fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.vptq_b200_abi_version.restype = ctypes.c_int
+        L.vptq_b200_last_error.restype = ctypes.c_char_p
+        L.vptq_b200_workspace_bytes.restype = ctypes.c_size_t
+        L.vptq_b200_workspace_bytes.argtypes = [ctypes.POINTER(LinearDesc), ctypes.c_int32, ctypes.c_int32]
+        vp, i64, i32, u32, sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_uint32, ctypes.c_size_t
+        dp = ctypes.POINTER(LinearDesc)
+        L.vptq_b200_quant_gemv.argtypes = [dp, vp, i64, vp, i64, i32, vp, sz, u32, vp]
+        L.vptq_b200_quant_gemm.argtypes = [dp, vp, i64, vp, i64, i32, vp, sz, u32, vp]
+        L.vptq_b200_dequant.argtypes = [dp, vp, vp, sz, vp]
+        L.vptq_b200_quant_gemv_v2.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp,
+                                              vp, vp, vp, sz, u32, vp]
+        L.vptq_b200_linear_host.argtypes = [dp, vp, vp, i32, vp, vp, vp, sz, u32, vp]
+        for f in ("vptq_b200_quant_gemv", "vptq_b200_quant_gemm", "vptq_b200_dequant", "vptq_b200_quant_gemv_v2",
+                  "vptq_b200_linear_host"):
+            getattr(L, f).restype = ctypes.c_int
+        if L.vptq_b200_abi_version() != ABI_VERSION:
+            raise RuntimeError(f"libvptq_b200.so ABI {L.vptq_b200_abi_version()} != expected {ABI_VERSION}")
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().vptq_b200_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (status {rc}): {last_error()}")
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    if dt == torch.float16:
+        return VPTQ_FP16
+    if dt == torch.bfloat16:
+        return VPTQ_BF16
+    raise RuntimeError(f"vptq_b200 supports float16 and bfloat16 tensors only, got {dt}")
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(name: str, t: Optional[torch.Tensor], contiguous: bool = True) -> None:
+    """The reference's CHECK_INPUT (csrc/util/common.h:11-19): CUDA + contiguous."""
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor (vptq_b200 has no CPU path)")
+    if contiguous and not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+
+
+def make_desc(*, dtype: torch.dtype, in_features: int, out_features: int, vector_len: int, num_centroids: int,
+              num_res_centroids: int, num_codebooks: int, group_size: int, outlier_size: int,
+              outlier_vector_len: int, num_outlier_centroids: int, indices: torch.Tensor,
+              centroids: torch.Tensor, res_centroids: Optional[torch.Tensor],
+              outlier_indices: Optional[torch.Tensor], outlier_centroids: Optional[torch.Tensor],
+              perm: Optional[torch.Tensor], weight_scale: Optional[torch.Tensor],
+              weight_bias: Optional[torch.Tensor], bias: Optional[torch.Tensor]) -> LinearDesc:
+    """Describe one layer's tensors for the C ABI.  Tensors are borrowed: keep them alive."""
+    if indices.dtype != torch.int32:
+        raise RuntimeError("`indices` must be packed int32 words (is_indice_packed=True); "
+                           "see vptq_b200.pack.pack_index")
+    for n, t in (("indices", indices), ("centroids", centroids), ("res_centroids", res_centroids),
+                 ("outlier_indices", outlier_indices), ("outlier_centroids", outlier_centroids), ("perm", perm),
+                 ("weight_scale", weight_scale), ("weight_bias", weight_bias), ("bias", bias)):
+        require_cuda(n, t)
+    if indices.dim() != 3:
+        raise RuntimeError(f"indices must be [num_codebooks, num_indices, packed_groupsize], got {tuple(indices.shape)}")
+    use_outlier = outlier_indices is not None and outlier_centroids is not None and outlier_size > 0
+    d = LinearDesc()
+    d.struct_size = ctypes.sizeof(LinearDesc)
+    d.dtype = dtype_code(dtype)
+    d.in_features, d.out_features = int(in_features), int(out_features)
+    d.vector_len, d.num_centroids = int(vector_len), int(num_centroids)
+    d.num_res_centroids = int(num_res_centroids) if res_centroids is not None else -1
+    d.num_codebooks, d.group_size = int(num_codebooks), int(group_size)
+    d.outlier_size = int(outlier_size) if use_outlier else 0
+    d.outlier_vector_len = int(outlier_vector_len)
+    d.num_outlier_centroids = int(num_outlier_centroids)
+    d.indices = _ptr(indices)
+    d.index_stride_codebook, d.index_stride_row = indices.stride(0), indices.stride(1)
+    d.centroids = _ptr(centroids)
+    d.centroid_stride = int(num_centroids) * int(vector_len)
+    d.res_centroids = _ptr(res_centroids)
+    d.res_centroid_stride = int(num_res_centroids) * int(vector_len) if res_centroids is not None else 0
+    d.outlier_indices = _ptr(outlier_indices) if use_outlier else None
+    d.outlier_centroids = _ptr(outlier_centroids) if use_outlier else None
+    d.perm = _ptr(perm)
+    d.weight_scale, d.weight_bias = _ptr(weight_scale), _ptr(weight_bias)
+    d.bias = _ptr(bias)
+    return d
+
+
+# one zero-initialised workspace per (device, stream): kernels leave it zeroed (include/vptq_b200.h)
+_workspaces: dict = {}
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def workspace_bytes(desc: LinearDesc, tokens: int, op: int) -> int:
+    return int(lib().vptq_b200_workspace_bytes(ctypes.byref(desc), int(tokens), int(op)))
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def quant_gemv(desc: LinearDesc, x2d: torch.Tensor, y2d: torch.Tensor, flags: int = 0) -> None:
+    dev = x2d.device
+    tokens = x2d.shape[0]
+    with torch.cuda.device(dev):
+        ws = workspace(dev, workspace_bytes(desc, tokens, OP_GEMV))
+        rc = lib().vptq_b200_quant_gemv(ctypes.byref(desc), x2d.data_ptr(), x2d.stride(0), y2d.data_ptr(),
+                                        y2d.stride(0), tokens, ws.data_ptr(), ws.numel(), flags, _stream(dev))
+    check(rc, "vptq_b200_quant_gemv")
+
+
+def quant_gemm(desc: LinearDesc, x2d: torch.Tensor, y2d: torch.Tensor, flags: int = 0) -> None:
+    dev = x2d.device
+    tokens = x2d.shape[0]
+    with torch.cuda.device(dev):
+        ws = workspace(dev, workspace_bytes(desc, tokens, OP_GEMM))
+        rc = lib().vptq_b200_quant_gemm(ctypes.byref(desc), x2d.data_ptr(), x2d.stride(0), y2d.data_ptr(),
+                                        y2d.stride(0), tokens, ws.data_ptr(), ws.numel(), flags, _stream(dev))
+    check(rc, "vptq_b200_quant_gemm")
+
+
+def dequant(desc: LinearDesc, w_out: torch.Tensor) -> None:
+    dev = w_out.device
+    with torch.cuda.device(dev):
+        ws = workspace(dev, workspace_bytes(desc, 1, OP_DEQUANT))
+        rc = lib().vptq_b200_dequant(ctypes.byref(desc), w_out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev))
+    check(rc, "vptq_b200_dequant")
