@@ -82,7 +82,11 @@ def test_dequant_matches_reference_cuda(ref, name):
     W = from_t(m.dequant())
     torch.cuda.synchronize()
     assert W.shape == W_ref.shape
-    # the reference rounds C+R to 16 bit, then fma-rounds again; ours rounds once: <= 2 ulp apart
+    # the reference rounds C+R to 16 bit and then fma-rounds again (csrc/kernels/dequant.cuh:87,98);
+    # ours evaluates in fp32 and rounds once.  |diff| <= ulp * (|W| + 0.5*|C+R|*|scale|), and
+    # |C+R|*|scale| <= |W| + |wbias|.
     ulp = 2.0 ** -10 if L.dtype == "fp16" else 2.0 ** -7
-    scale = np.abs(W_ref).max()
-    assert np.all(np.abs(W - W_ref) <= 2 * ulp * np.maximum(np.abs(W_ref), 0.05 * scale))
+    wb = np.abs(vo.to_f32(L.weight_bias, L.dtype)).max()
+    bound = 2 * ulp * (np.abs(W_ref) + wb) + 1e-7
+    bad = np.abs(W - W_ref) > bound
+    assert not bad.any(), f"{int(bad.sum())} of {bad.size} elements beyond the double-rounding bound"

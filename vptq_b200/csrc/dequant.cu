@@ -140,7 +140,8 @@ int launch_v(const DequantParams& p, int v, cudaStream_t stream) {
 }  // namespace
 
 size_t dequant_workspace_bytes(const vptq_linear_desc& d) {
-  return d.perm ? align_up(size_t(d.in_features) * 2, 256) : 0;
+  // the inverse permutation is scratch: it goes behind the zero-at-rest counter region
+  return d.perm ? kCounterRegionBytes + align_up(size_t(d.in_features) * 2, 256) : 0;
 }
 
 int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size_t workspace_bytes,
@@ -167,21 +168,13 @@ int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size
       set_error("dequant: workspace %zu bytes < required %zu (inverse permutation)", workspace_bytes, need);
       return VPTQ_ERR_WORKSPACE;
     }
-    uint16_t* inv = reinterpret_cast<uint16_t*>(workspace);
+    uint16_t* inv = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(workspace) + kCounterRegionBytes);
     invert_perm_kernel<<<(d.in_features + 255) / 256, 256, 0, stream>>>(d.perm, inv, d.in_features);
     p.inv_perm = inv;
   }
   const int rc = d.dtype == VPTQ_FP16 ? launch_v<__half>(p, d.vector_len, stream)
                                       : launch_v<__nv_bfloat16>(p, d.vector_len, stream);
   if (rc) return rc;
-  if (d.perm) {
-    // the GEMV's split-K counters share this workspace and expect it zeroed at rest
-    cudaError_t e = cudaMemsetAsync(workspace, 0, dequant_workspace_bytes(d), stream);
-    if (e != cudaSuccess) {
-      set_error("dequant: workspace reset: %s", cudaGetErrorString(e));
-      return VPTQ_ERR_CUDA;
-    }
-  }
   return 0;
 }
 

@@ -141,7 +141,11 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
     return VPTQ_ERR_UNSUPPORTED;
   }
 
-  pl.ws_counters_bytes = align_up(size_t(Ro) * 4, 256);
+  if (Ro > kMaxIndexRows) {
+    set_error("gemv: %d index rows exceed the supported maximum %d", Ro, kMaxIndexRows);
+    return VPTQ_ERR_UNSUPPORTED;
+  }
+  pl.ws_counters_bytes = kCounterRegionBytes;
   pl.ws_partials_bytes = pl.nch > 1 ? align_up(size_t(pl.nch) * pl.nt * Ro * v * 4, 256) : 0;
   *out = pl;
   return 0;

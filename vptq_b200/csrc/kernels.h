@@ -28,6 +28,13 @@ static inline int ilog2(int64_t v) {
 }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// Workspace convention shared by every op: bytes [0, kCounterRegionBytes) hold the GEMV's split-K
+// row counters and are the ONLY part that must be zero at rest; everything behind is scratch that
+// each op overwrites before reading.  The region's extent is fixed so that it never depends on
+// which layer used the workspace last.
+constexpr int kMaxIndexRows = 65536;
+constexpr size_t kCounterRegionBytes = size_t(kMaxIndexRows) * 4;
+
 // -------------------------------------------------------------------------------------------
 // decode GEMV
 // -------------------------------------------------------------------------------------------
@@ -53,7 +60,7 @@ struct GemvPlan {
   uint32_t stage_bytes;
   uint32_t smem_bytes;
   // workspace carve-up
-  size_t ws_counters_bytes;  // Ro uint32 (zero at rest)
+  size_t ws_counters_bytes;  // fixed 256 KiB region of uint32 row counters (zero at rest)
   size_t ws_partials_bytes;  // nch * nt * Ro*v floats (only when nch > 1)
 };
 
