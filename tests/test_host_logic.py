@@ -170,8 +170,12 @@ def test_c_abi_validation_and_workspace_without_gpu():
     from vptq_b200 import native
     L = native.lib()
     ws = L.vptq_b200_workspace_bytes(ctypes.byref(_desc()), 1, native.OP_GEMV)
-    # fixed 256 KiB counter region + 4 column chunks x 4096 fp32 partial sums (B200 geometry assumed without a GPU)
-    assert ws == 65536 * 4 + 4 * 4096 * 4
+    # fixed 256 KiB zero-at-rest counter region; this layer reduces its column chunks through a
+    # thread-block cluster, so no global partial-sum scratch (B200 geometry assumed without a GPU)
+    assert ws == 65536 * 4
+    # 16 codebook groups -> more than 8 chunks -> global-memory split-K scratch behind the counters
+    many = _desc(num_codebooks=16, group_size=256, index_stride_row=192, index_stride_codebook=512 * 192)
+    assert L.vptq_b200_workspace_bytes(ctypes.byref(many), 1, native.OP_GEMV) == 65536 * 4 + 16 * 4096 * 4
     for bad, msg in ((dict(vector_len=7), "vector_len"), (dict(num_centroids=1000), "power of two"),
                      (dict(group_size=4000), "in_features"), (dict(index_stride_row=100), "index_stride_row"),
                      (dict(res_centroids=0), "res_centroids"), (dict(dtype=3), "dtype"),

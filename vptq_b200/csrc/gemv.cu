@@ -1,6 +1,8 @@
 // Host side of the decode GEMV: work decomposition (GemvPlan), shared-memory carve-up, launch.
 #include <algorithm>
+#include <map>
 #include <mutex>
+#include <tuple>
 #include <unordered_set>
 
 #include "gemv_kernel.cuh"
@@ -9,17 +11,20 @@ namespace vptq_b200 {
 
 namespace {
 
-constexpr int kMaxChunkCols = 4096;   // bounds the x' slice in shared memory (16 KB per token)
-constexpr int kSegFields = 512;       // index fields per ring stage
-constexpr int kSmemReserve = 2048;    // head-room below the opt-in limit
+constexpr int kMaxChunkCols = 4096;      // bounds the x' slice in shared memory (16 KB per token)
+constexpr int kSegFields = 512;          // index fields per ring stage
+constexpr int kSmemReserve = 2048;       // head-room below the opt-in limit
+constexpr int kSmemPerSm = 233472;       // 228 KB per SM, 1 KB of it reserved per resident CTA
+constexpr int kMaxClusterPartBytes = 16384;
 
 bool supported_vec_len(int v) { return v == 2 || v == 4 || v == 6 || v == 8 || v == 10 || v == 12 || v == 16; }
 
-std::mutex g_attr_mutex;
+std::mutex g_mutex;
 std::unordered_set<const void*> g_attr_done;
+std::map<std::tuple<const void*, int, int, int>, int> g_max_clusters;
 
 int ensure_smem_attr(const void* fn, int bytes) {
-  std::lock_guard<std::mutex> lock(g_attr_mutex);
+  std::lock_guard<std::mutex> lock(g_mutex);
   if (g_attr_done.count(fn)) return 0;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) {
@@ -30,10 +35,41 @@ int ensure_smem_attr(const void* fn, int bytes) {
   return 0;
 }
 
+GemvKernelFn pick_kernel(const vptq_linear_desc& d, int nt, bool main_smem) {
+  const bool res = d.num_res_centroids > 0;
+  return d.vector_len == 8 ? gemv_kernel_v8(d.dtype, nt, main_smem, res)
+                           : gemv_kernel_vx(d.dtype, d.vector_len, main_smem, res);
+}
+
+// how many clusters of `csize` CTAs (threads, smem each) the device can hold at once; <= 0: unknown
+int max_active_clusters(const void* fn, int csize, int threads, int smem, int optin) {
+  {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    auto it = g_max_clusters.find({fn, csize, threads, smem});
+    if (it != g_max_clusters.end()) return it->second;
+  }
+  if (ensure_smem_attr(fn, optin)) return -1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(csize));
+  cfg.blockDim = dim3(unsigned(threads));
+  cfg.dynamicSmemBytes = size_t(smem);
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = unsigned(csize), at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+  cfg.attrs = at, cfg.numAttrs = 1;
+  int n = -1;
+  if (cudaOccupancyMaxActiveClusters(&n, fn, &cfg) != cudaSuccess) {
+    cudaGetLastError();
+    n = -1;
+  }
+  std::lock_guard<std::mutex> lock(g_mutex);
+  g_max_clusters[{fn, csize, threads, smem}] = n;
+  return n;
+}
+
 }  // namespace
 
 int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev, GemvPlan* out) {
-  GemvPlan pl{};
   const int v = d.vector_len, G = d.num_codebooks, gs = d.group_size;
   const int Ro = (d.out_features + v - 1) / v;
   const int ib = ilog2(d.num_centroids);
@@ -41,114 +77,122 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
   const int b = ib + rb;
   const int S = (d.outlier_size > 0 && d.outlier_indices) ? d.outlier_size : 0;
   const int EB = 2 * v;
-
-  pl.nt = (v == 8) ? (tokens >= 4 ? 4 : (tokens >= 2 ? 2 : 1)) : 1;
-  pl.seg_fields = kSegFields;
-  pl.stage_bytes = uint32_t(align_up(size_t(pl.seg_fields) * b / 8 + 16, 16));
-
-  // ---- codebook placement -------------------------------------------------------------------
-  const int budget = dev.smem_optin - kSmemReserve;
-  const size_t main_bytes = size_t(d.num_centroids) * EB;
-  const size_t res_bytes = rb ? size_t(d.num_res_centroids) * EB : 0;
-  pl.res_rep = (rb && v == 8 && res_bytes * 8 <= 32768) ? 8 : 1;
-  pl.main_rep = 1;
-  pl.main_in_smem = 0;
-  if (main_bytes <= 131072) {
-    pl.main_in_smem = 1;
-    if (v == 8 && main_bytes * 8 <= 32768) pl.main_rep = 8;
-  }
-
-  // ---- column chunks and the grid -----------------------------------------------------------
-  // Candidates: cpg chunks per group, chunk width a multiple of 128 columns.  Cost model: the SM
-  // with the most (row, chunk) units bounds the kernel; more CTAs per chunk than rows is waste;
-  // fewer rows per CTA than warps leaves the gather pipeline short of parallelism.
   const int sms = dev.sm_count;
-  int best_cpg = 1;
-  double best_cost = 1e300;
-  for (int cpg = 1; cpg <= 64; cpg *= 2) {
-    int cc = int(align_up(size_t((gs + cpg - 1) / cpg), 128));
-    if (cc > kMaxChunkCols) continue;
-    if (cpg > 1 && cc < 256) break;
-    const int real_cpg = (gs + cc - 1) / cc;
-    const int nch = G * real_cpg;
-    if (nch > sms) break;
-    const int cpc = std::max(1, std::min(sms / nch, Ro));
-    const int rows_cta = (Ro + cpc - 1) / cpc;
-    double cost = double(rows_cta) * cc;                  // fields the busiest SM streams
-    cost += 600.0 + 0.35 * cc;                            // per-CTA prologue (x' gather, codebooks)
-    cost += 64.0 * rows_cta;                              // per-unit epilogue (reduce, fence, atomic)
-    if (rows_cta < 8) cost *= 1.0 + 0.08 * (8 - rows_cta);  // too few warps busy per SM
-    if (cost < best_cost) best_cost = cost, best_cpg = real_cpg, pl.chunk_cols = cc;
-  }
-  if (best_cost == 1e300) {  // very wide single group: fall back to the widest legal chunk
-    pl.chunk_cols = kMaxChunkCols;
-    best_cpg = (gs + kMaxChunkCols - 1) / kMaxChunkCols;
-  }
-  pl.cpg = best_cpg;
-  pl.nch = G * pl.cpg;
-  if (pl.nch > sms) {
-    set_error("gemv: %d column chunks exceed %d SMs (num_codebooks=%d)", pl.nch, sms, G);
-    return VPTQ_ERR_UNSUPPORTED;
-  }
-  pl.cpc = std::max(1, std::min(sms / pl.nch, Ro));
-  pl.grid = pl.nch * pl.cpc;
-
-  // ---- shared memory carve-up ----------------------------------------------------------------
-  auto carve = [&](int warps, int stages, bool main_smem) -> size_t {
-    size_t off = 0;
-    pl.off_bars = uint32_t(off);
-    off += align_up(size_t(1 + warps * stages) * 8, 128);
-    pl.off_cbias = uint32_t(off);
-    off += align_up(size_t(pl.nt) * (1 + warps) * 4, 128);
-    const int n_all = pl.chunk_cols + S;
-    pl.sx_stride = int(align_up(size_t(n_all), 32));
-    pl.off_pcol = uint32_t(off);
-    off += align_up(size_t(n_all) * 2, 128);
-    pl.off_wb = uint32_t(off);
-    off += align_up(size_t(n_all) * 4, 128);
-    pl.off_sx = uint32_t(off);
-    off += align_up(size_t(pl.nt) * pl.sx_stride * 4, 128);
-    pl.off_res = uint32_t(off);
-    off += align_up(res_bytes * pl.res_rep, 128);
-    pl.off_main = uint32_t(off);
-    if (main_smem) off += align_up(main_bytes * pl.main_rep, 128);
-    pl.off_ring = uint32_t(off);
-    off += size_t(warps) * stages * pl.stage_bytes;
-    return off;
-  };
-  // prefer 16 warps x 4 stages; shed stages, then warps, then the smem-resident main codebook
-  static const int kWarps[] = {16, 8};
-  static const int kStages[] = {4, 3, 2};
-  bool placed = false;
-  for (int pass = 0; pass < 2 && !placed; ++pass) {
-    const bool main_smem = pl.main_in_smem && pass == 0;
-    for (int w : kWarps) {
-      for (int s : kStages) {
-        const size_t need = carve(w, s, main_smem);
-        if (need <= size_t(budget)) {
-          pl.threads = w * 32, pl.stages = s, pl.smem_bytes = uint32_t(need);
-          pl.main_in_smem = main_smem;
-          if (!main_smem) pl.main_rep = 1;
-          placed = true;
-          break;
-        }
-      }
-      if (placed) break;
-    }
-  }
-  if (!placed) {
-    set_error("gemv: residual codebook of %zu bytes does not fit shared memory", res_bytes);
-    return VPTQ_ERR_UNSUPPORTED;
-  }
-
   if (Ro > kMaxIndexRows) {
     set_error("gemv: %d index rows exceed the supported maximum %d", Ro, kMaxIndexRows);
     return VPTQ_ERR_UNSUPPORTED;
   }
-  pl.ws_counters_bytes = kCounterRegionBytes;
-  pl.ws_partials_bytes = pl.nch > 1 ? align_up(size_t(pl.nch) * pl.nt * Ro * v * 4, 256) : 0;
-  *out = pl;
-  return 0;
+
+  GemvPlan pl{};
+  pl.nt = (v == 8) ? (tokens >= 4 ? 4 : (tokens >= 2 ? 2 : 1)) : 1;
+  pl.seg_fields = kSegFields;
+  pl.stage_bytes = uint32_t(align_up(size_t(pl.seg_fields) * b / 8 + 16, 16));
+
+  const size_t main_bytes = size_t(d.num_centroids) * EB;
+  const size_t res_bytes = rb ? size_t(d.num_res_centroids) * EB : 0;
+  pl.res_rep = (rb && v == 8 && res_bytes * 8 <= 32768) ? 8 : 1;
+  const bool main_fits = main_bytes <= 131072;
+  const int main_rep_smem = (v == 8 && main_bytes * 8 <= 32768) ? 8 : 1;
+
+  // One attempt = (CTAs per SM, warps per CTA, main codebook in smem?).  First fit wins:
+  // two 8-warp CTAs per SM (prologue of one overlaps the main loop of the other, and of the
+  // previous kernel's tail under PDL), else one 16-warp CTA, shedding ring stages before that.
+  struct Attempt { int ctas_per_sm, warps; bool main_smem; };
+  const Attempt attempts[] = {{2, 8, true}, {1, 16, true}, {1, 8, true}, {2, 8, false}, {1, 16, false}, {1, 8, false}};
+  for (const Attempt& a : attempts) {
+    if (a.main_smem && !main_fits) continue;
+    const int slots = sms * a.ctas_per_sm;
+    const int smem_limit = a.ctas_per_sm == 1 ? dev.smem_optin - kSmemReserve : kSmemPerSm / 2 - 1024 - 512;
+
+    // ---- column chunks: cpg per codebook group, width a multiple of 128 columns ----------------
+    // cost ~ fields streamed by the busiest CTA + per-CTA prologue + per-row epilogue; chunk
+    // counts up to 8 reduce through the cluster, more than 8 through global memory (dearer).
+    int best_cpg = 0, best_cc = 0;
+    double best_cost = 1e300;
+    for (int cpg = 1; cpg <= 64; cpg *= 2) {
+      const int cc = int(align_up(size_t((gs + cpg - 1) / cpg), 128));
+      if (cc > kMaxChunkCols) continue;
+      if (cpg > 1 && cc < 256) break;
+      const int real_cpg = (gs + cc - 1) / cc;
+      const int nch = G * real_cpg;
+      if (nch > slots) break;
+      const int cpc = std::max(1, std::min(slots / nch, Ro));
+      const int rows_cta = (Ro + cpc - 1) / cpc;
+      double cost = double(rows_cta) * cc + 600.0 + 0.35 * cc;
+      cost += (nch <= 8 ? 24.0 : 96.0) * rows_cta;
+      if (rows_cta < a.warps / 2) cost *= 1.0 + 0.6 * (a.warps / 2 - rows_cta) / double(a.warps);
+      if (cost < best_cost) best_cost = cost, best_cpg = real_cpg, best_cc = cc;
+    }
+    if (!best_cpg) {  // very wide single group: the widest legal chunk
+      best_cc = kMaxChunkCols;
+      best_cpg = (gs + kMaxChunkCols - 1) / kMaxChunkCols;
+    }
+    pl.chunk_cols = best_cc, pl.cpg = best_cpg, pl.nch = G * best_cpg;
+    if (pl.nch > slots) continue;
+    pl.cpc = std::max(1, std::min(slots / pl.nch, Ro));
+    const int rows_cta = (Ro + pl.cpc - 1) / pl.cpc;
+    // cluster reduce needs the leader to hold every row's chunk partials; allow for a smaller grid
+    // (cpc is clamped to the co-schedulable cluster count below) with 25% slack
+    const size_t part_bytes = size_t(rows_cta + rows_cta / 4 + 1) * pl.nch * pl.nt * v * 4;
+    pl.cluster = (pl.nch >= 2 && pl.nch <= 8 && part_bytes <= kMaxClusterPartBytes) ? 1 : 0;
+    pl.main_in_smem = a.main_smem ? 1 : 0;
+    pl.main_rep = a.main_smem ? main_rep_smem : 1;
+    pl.ctas_per_sm = a.ctas_per_sm;
+
+    // ---- shared memory carve-up ----------------------------------------------------------------
+    auto carve = [&](int warps, int stages) -> size_t {
+      size_t off = 0;
+      pl.off_bars = uint32_t(off);
+      off += align_up(size_t(1 + warps * stages) * 8, 128);
+      pl.off_cbias = uint32_t(off);
+      off += align_up(size_t(pl.nt) * (1 + warps) * 4, 128);
+      const int n_all = pl.chunk_cols + S;
+      pl.sx_stride = int(align_up(size_t(n_all), 32));
+      pl.off_pcol = uint32_t(off);
+      off += align_up(size_t(n_all) * 2, 128);
+      pl.off_wb = uint32_t(off);
+      off += align_up(size_t(n_all) * 4, 128);
+      pl.off_sx = uint32_t(off);
+      off += align_up(size_t(pl.nt) * pl.sx_stride * 4, 128);
+      pl.off_part = uint32_t(off);
+      if (pl.cluster) off += align_up(part_bytes, 128);
+      pl.off_res = uint32_t(off);
+      off += align_up(res_bytes * pl.res_rep, 128);
+      pl.off_main = uint32_t(off);
+      if (a.main_smem) off += align_up(main_bytes * pl.main_rep, 128);
+      pl.off_ring = uint32_t(off);
+      off += size_t(warps) * stages * pl.stage_bytes;
+      return off;
+    };
+    bool placed = false;
+    for (int stages : {4, 3, 2}) {
+      const size_t need = carve(a.warps, stages);
+      if (need <= size_t(smem_limit)) {
+        pl.threads = a.warps * 32, pl.stages = stages, pl.smem_bytes = uint32_t(need);
+        placed = true;
+        break;
+      }
+    }
+    if (!placed) continue;
+
+    // ---- clusters must all be co-resident: a second wave would double the kernel ----------------
+    if (pl.cluster && dev.device >= 0) {
+      GemvKernelFn fn = pick_kernel(d, pl.nt, a.main_smem);
+      const int n = fn ? max_active_clusters(reinterpret_cast<const void*>(fn), pl.nch, pl.threads,
+                                             int(pl.smem_bytes), dev.smem_optin)
+                       : -1;
+      if (n > 0 && n < pl.cpc) pl.cpc = n;
+      const int rows2 = (Ro + pl.cpc - 1) / pl.cpc;
+      if (size_t(rows2) * pl.nch * pl.nt * v * 4 > align_up(part_bytes, 128)) pl.cluster = 0;  // (never with 25% slack)
+    }
+    pl.grid = pl.nch * pl.cpc;
+    pl.ws_counters_bytes = kCounterRegionBytes;
+    pl.ws_partials_bytes = (pl.nch > 1 && !pl.cluster) ? align_up(size_t(pl.nch) * pl.nt * Ro * v * 4, 256) : 0;
+    *out = pl;
+    return 0;
+  }
+  set_error("gemv: no shared-memory layout fits (residual codebook %zu bytes, %d column groups)", res_bytes, G);
+  return VPTQ_ERR_UNSUPPORTED;
 }
 
 int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void* y, int64_t y_stride,
@@ -161,8 +205,8 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
   }
   GemvPlan pl;
   if (int rc = gemv_make_plan(d, tokens, *dev, &pl)) return rc;
-  const size_t need = pl.ws_counters_bytes + pl.ws_partials_bytes;
-  if (workspace_bytes < need || (need && !workspace)) {
+  const size_t need = pl.ws_partials_bytes ? pl.ws_counters_bytes + pl.ws_partials_bytes : 0;
+  if (need && (workspace_bytes < need || !workspace)) {
     set_error("gemv: workspace %zu bytes < required %zu", workspace_bytes, need);
     return VPTQ_ERR_WORKSPACE;
   }
@@ -192,20 +236,19 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
   p.bias = d.bias;
   p.x_stride = x_stride, p.y_stride = y_stride;
   p.counters = reinterpret_cast<uint32_t*>(workspace);
-  p.partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + pl.ws_counters_bytes);
+  p.partials = workspace ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + pl.ws_counters_bytes)
+                         : nullptr;
   p.idx_tma_ok = ((reinterpret_cast<uintptr_t>(d.indices) & 15u) == 0 && (d.index_stride_row & 3) == 0 &&
                   (d.index_stride_codebook & 3) == 0)
                      ? 1
                      : 0;
   p.plan = pl;
 
-  const bool res = p.rb > 0;
   const size_t esz = 2;
   for (int t0 = 0; t0 < tokens;) {
     int nt = pl.nt;
     while (nt > tokens - t0) nt >>= 1;  // tail passes: 4 -> 2 -> 1
-    GemvKernelFn fn = d.vector_len == 8 ? gemv_kernel_v8(d.dtype, nt, pl.main_in_smem != 0, res)
-                                        : gemv_kernel_vx(d.dtype, d.vector_len, pl.main_in_smem != 0, res);
+    GemvKernelFn fn = pick_kernel(d, nt, pl.main_in_smem != 0);
     if (!fn) {
       set_error("gemv: no kernel for dtype=%d v=%d nt=%d", d.dtype, d.vector_len, nt);
       return VPTQ_ERR_UNSUPPORTED;
@@ -213,26 +256,33 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
     if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(fn), dev->smem_optin)) return rc;
     p.x = reinterpret_cast<const uint8_t*>(x) + size_t(t0) * x_stride * esz;
     p.y = reinterpret_cast<uint8_t*>(y) + size_t(t0) * y_stride * esz;
-    // the smem carve-up was sized for pl.nt tokens; a narrower tail pass fits a fortiori, but the
-    // partial-sum layout depends on nt, so the kernel is told the pass width through the template.
+    // the carve-up was sized for pl.nt tokens; a narrower tail pass fits a fortiori (the kernel's
+    // partial-sum indexing uses its own template NT consistently on both sides)
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(pl.grid));
     cfg.blockDim = dim3(unsigned(pl.threads));
     cfg.dynamicSmemBytes = pl.smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     int nattr = 0;
     if (flags & VPTQ_FLAG_PDL) {
       attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
       attr[nattr].val.programmaticStreamSerializationAllowed = 1;
       ++nattr;
     }
+    if (pl.cluster) {
+      attr[nattr].id = cudaLaunchAttributeClusterDimension;
+      attr[nattr].val.clusterDim.x = unsigned(pl.nch);
+      attr[nattr].val.clusterDim.y = 1;
+      attr[nattr].val.clusterDim.z = 1;
+      ++nattr;
+    }
     cfg.attrs = attr;
     cfg.numAttrs = unsigned(nattr);
     cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
     if (e != cudaSuccess) {
-      set_error("gemv launch (grid=%d block=%d smem=%u): %s", pl.grid, pl.threads, pl.smem_bytes,
-                cudaGetErrorString(e));
+      set_error("gemv launch (grid=%d block=%d smem=%u cluster=%d): %s", pl.grid, pl.threads, pl.smem_bytes,
+                pl.cluster ? pl.nch : 1, cudaGetErrorString(e));
       return VPTQ_ERR_CUDA;
     }
     t0 += nt;

@@ -7,11 +7,19 @@
 // csrc/kernels/quant_gemv.cuh:11-186, with the three hoists it does not make: x' is formed once
 // per CTA instead of per (row, column); the weight_bias term is a per-token scalar added in the
 // epilogue; accumulation is fp32.)  Nothing here is derived from the reference's kernel
-// structure: rows are owned by warps, the packed index words of a row arrive through a per-warp
-// ring of 1-D TMA bulk copies (cp.async.bulk + mbarrier), codebooks are staged in shared memory
-// (bank-group replicated when small) or gathered through L1/L2 with an evict_last policy, and
-// the split-K reduction is a deterministic "last CTA sums in chunk order" epilogue instead of a
-// second kernel.
+// structure:
+//   * a CTA owns one column chunk (its x' slice and codebooks are staged once) and a strided set
+//     of index rows; every warp owns whole rows and keeps the v partial sums in registers;
+//   * the packed index words of a row arrive through a per-warp ring of 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier, L2 evict_first);
+//   * codebooks are staged in shared memory (bank-group replicated when small, so 128-bit gathers
+//     are conflict-free) or, when they do not fit (65536 x 16 B = 1 MiB), gathered through L1/L2
+//     with an evict_last policy, 8 independent 16-byte gathers in flight per lane;
+//   * the split-K reduction over column chunks runs inside a thread-block cluster: every CTA
+//     pushes its partial sums into the leader's shared memory (st.shared::cluster) and one
+//     cluster barrier later the leader sums them in chunk order and writes y.  No second kernel
+//     (the reference launches `sum(-1)`, csrc/quant_gemv.cu:235), no global atomics or fences.
+//     Layers cut into more than 8 chunks use a global-memory variant of the same scheme.
 #pragma once
 
 #include "common.cuh"
@@ -37,7 +45,7 @@ struct GemvParams {
   const void* x;
   void* y;
   int64_t x_stride, y_stride;  // elements per token
-  // split-K workspace
+  // global split-K workspace (only when the plan does not use a cluster)
   float* partials;
   uint32_t* counters;
   // shapes
@@ -47,7 +55,7 @@ struct GemvParams {
   GemvPlan plan;
 };
 
-// accumulate x * (c + r) into acc[V] for one gathered (main, residual) entry pair
+// acc[e] += xv * (c[e] + r[e]) for one gathered (main, residual) entry pair, fp32 arithmetic
 template <typename T, int V, bool RES>
 __device__ __forceinline__ void fma_entry(float (&acc)[V], float xv, const uint32_t (&cw)[V / 2],
                                           const uint32_t (&rw)[V / 2]) {
@@ -55,7 +63,7 @@ __device__ __forceinline__ void fma_entry(float (&acc)[V], float xv, const uint3
   for (int i = 0; i < V / 2; ++i) {
     float2 c = DT<T>::unpack2(cw[i]);
     if constexpr (RES) {
-      float2 r = DT<T>::unpack2(rw[i]);
+      const float2 r = DT<T>::unpack2(rw[i]);
       c.x += r.x;
       c.y += r.y;
     }
@@ -64,15 +72,50 @@ __device__ __forceinline__ void fma_entry(float (&acc)[V], float xv, const uint3
   }
 }
 
+// Sum acc[0..V) over the 32 lanes.  Returns, in lane e (e < V), the total of acc[e].
+// V == 8: recursive halving -- 4+2+1 exchanges that each halve the live values, then two plain
+// butterfly steps: 9 shuffles instead of 40.
+template <int V>
+__device__ __forceinline__ float warp_reduce_to_lane(float (&acc)[V], int lane) {
+  if constexpr (V == 8) {
+    float a4[4], a2[2];
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float keep = h16 ? acc[i + 4] : acc[i], send = h16 ? acc[i] : acc[i + 4];
+      a4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float keep = h8 ? a4[i + 2] : a4[i], send = h8 ? a4[i] : a4[i + 2];
+      a2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    const float keep = h4 ? a2[1] : a2[0], send = h4 ? a2[0] : a2[1];
+    float v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    // lanes with bits (16,8,4) = (b2,b1,b0) now hold output e = 4*b2 + 2*b1 + b0; move it to lane e
+    return __shfl_sync(0xffffffffu, v, ((lane & 4) << 2) | ((lane & 2) << 2) | ((lane & 1) << 2));
+  } else {
+    float mine = 0.f;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float v = warp_sum(acc[e]);
+      if (lane == e) mine = v;
+    }
+    return mine;
+  }
+}
+
 template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
 __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int U = 4;              // fields per lane in flight
-  constexpr int EB = 2 * V;         // bytes per codebook entry
+  constexpr int U = (NT == 1 && V <= 8) ? 8 : 4;  // independent codebook gathers in flight per lane
+  constexpr int EB = 2 * V;                       // bytes per codebook entry
   const GemvPlan& pl = p.plan;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int chunk = blockIdx.x % pl.nch;
+  const int chunk = blockIdx.x % pl.nch;  // == %cluster_ctarank when launched as a cluster
   const int cta_in_chunk = blockIdx.x / pl.nch;
   const int g = chunk / pl.cpg, cig = chunk % pl.cpg;
   const int f0 = cig * pl.chunk_cols;
@@ -87,6 +130,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   uint16_t* s_pcol = reinterpret_cast<uint16_t*>(smem + pl.off_pcol);
   float* s_wb = reinterpret_cast<float*>(smem + pl.off_wb);
   float* sx = reinterpret_cast<float*>(smem + pl.off_sx);
+  float* s_part = reinterpret_cast<float*>(smem + pl.off_part);
   uint8_t* s_res = smem + pl.off_res;
   uint8_t* s_main = smem + pl.off_main;
   uint8_t* ring = smem + pl.off_ring + warp * pl.stages * pl.stage_bytes;
@@ -103,7 +147,8 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     fence_mbar_init();
   }
   __syncthreads();
-  pdl_launch_dependents();  // the next kernel may start its own weight-only prologue now
+  if (pl.cluster) cluster_arrive();  // phase 0: "this CTA is running" (waited before the first DSMEM store)
+  pdl_launch_dependents();           // the next kernel may start its own weight-only prologue now
 
   const uint64_t pol_stream = policy_evict_first();
   const uint64_t pol_keep = policy_evict_last();
@@ -144,7 +189,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   for (int q = 0; q < npre; ++q) issue(q);
 
   // -------- codebooks -> shared memory (weights only: legal before the PDL wait) -----------
-  // rep == 1: one TMA bulk copy.  rep == 8: entry i is stored 8 times, copy k at 16-byte slot
+  // rep == 1: TMA bulk copies.  rep == 8: entry i is stored 8 times, copy k at 16-byte slot
   // i*8+k, so that lane L reads slot i*8 + (L & 7): the 8 lanes of a quarter-warp always hit
   // 8 different 16-byte bank groups -> conflict-free 128-bit gathers.
   uint32_t cb_tx = 0;
@@ -220,6 +265,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   }
   __syncthreads();
   if constexpr (RES || MAIN_SMEM) mbar_wait(cb_bar, 0);
+  if (pl.cluster) cluster_wait();  // every CTA of the cluster has started: its smem may be written
 
   // -------- main loop ------------------------------------------------------------------------
   const uint32_t fmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
@@ -229,6 +275,9 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   const uint32_t s_main_lane = smem_u32(s_main) + (pl.main_rep > 1 ? (lane & 7) * EB : 0);
   const uint32_t s_res_lane = smem_u32(s_res) + (pl.res_rep > 1 ? (lane & 7) * EB : 0);
   const uint8_t* cent_bytes = reinterpret_cast<const uint8_t*>(cent_g);
+  const uint32_t part_leader = pl.cluster ? mapa_shared(smem_u32(s_part), 0) : 0u;
+  const T* bias = reinterpret_cast<const T*>(p.bias);
+  T* y = reinterpret_cast<T*>(p.y);
 
   float acc[NT][V];
 #pragma unroll
@@ -238,7 +287,8 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
 
   for (int q = 0; q < total; ++q) {
     const int u = q / nseg, s = q - u * nseg;
-    const int r = cta_in_chunk + pl.cpc * (warp + nwarps * u);
+    const int krow = warp + nwarps * u;  // position of the row in this CTA's row list
+    const int r = cta_in_chunk + pl.cpc * krow;
     const int seg0 = s * pl.seg_fields;  // first field of the segment, relative to the chunk
     const int nf = min(pl.seg_fields, ncols - seg0);
     const int st = q % pl.stages;
@@ -247,39 +297,40 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     const float* sxs = sx + seg0;
 
     for (int jb = 0; jb < nf; jb += 32 * U) {
-      uint32_t mi[U], ri[U];
-      float xv[U][NT];
+      uint32_t fld[U];
 #pragma unroll
       for (int k = 0; k < U; ++k) {
         const int j = jb + 32 * k + lane;
-        const bool valid = j < nf;
         const uint32_t bit = uint32_t(j) * uint32_t(b);
         const uint32_t w = bit >> 5;
-        uint32_t f = __funnelshift_r(sw[w], sw[w + 1], bit & 31u) & fmask;
-        f = valid ? f : 0u;  // out-of-range lanes gather entry 0 and multiply by zero
-        mi[k] = f & imask;
-        ri[k] = f >> p.ib;
-#pragma unroll
-        for (int t = 0; t < NT; ++t) xv[k][t] = valid ? sxs[t * pl.sx_stride + j] : 0.f;
+        const uint32_t f = __funnelshift_r(sw[w], sw[w + 1], bit & 31u) & fmask;
+        fld[k] = j < nf ? f : 0u;  // out-of-range lanes gather entry 0 and multiply by zero
       }
-      uint32_t cw[U][V / 2], rw[U][V / 2];
+      uint32_t cw[U][V / 2];
 #pragma unroll
       for (int k = 0; k < U; ++k) {
-        if constexpr (MAIN_SMEM) lds_entry<V>(cw[k], s_main_lane + mi[k] * main_stride);
-        else ldg_entry<V>(cw[k], cent_bytes + size_t(mi[k]) * EB, pol_keep);
-        if constexpr (RES) lds_entry<V>(rw[k], s_res_lane + ri[k] * res_stride);
+        const uint32_t mi = fld[k] & imask;
+        if constexpr (MAIN_SMEM) lds_entry<V>(cw[k], s_main_lane + mi * main_stride);
+        else ldg_entry<V>(cw[k], cent_bytes + size_t(mi) * EB, pol_keep);
       }
 #pragma unroll
-      for (int k = 0; k < U; ++k)
+      for (int k = 0; k < U; ++k) {
+        const int j = jb + 32 * k + lane;
+        uint32_t rw[V / 2];
+        if constexpr (RES) lds_entry<V>(rw, s_res_lane + (fld[k] >> p.ib) * res_stride);
 #pragma unroll
-        for (int t = 0; t < NT; ++t) fma_entry<T, V, RES>(acc[t], xv[k][t], cw[k], rw[k]);
+        for (int t = 0; t < NT; ++t) {
+          const float xv = j < nf ? sxs[t * pl.sx_stride + j] : 0.f;
+          fma_entry<T, V, RES>(acc[t], xv, cw[k], rw);
+        }
+      }
     }
     __syncwarp();  // every lane's index words are in registers (its gathers depended on them)
     if (q + pl.stages < total) issue(q + pl.stages);
 
     if (s != nseg - 1) continue;
 
-    // ---- row finished: outlier columns (owned by chunk 0), reduction, store ---------------
+    // ---- row finished: outlier columns (owned by chunk 0), reduction, hand-off -------------
     if (owns_outliers) {
       const T* ocb = reinterpret_cast<const T*>(p.outlier_cb);
       const float* sxo = sx + ncols;
@@ -300,40 +351,41 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
         }
       }
     }
-    // butterfly: afterwards every lane holds the row's full sums; lane e keeps output e
-    float mine[NT];
+    float mine[NT];  // lane e < V: sum of output e of this row over the chunk's columns
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      mine[t] = 0.f;
+      mine[t] = warp_reduce_to_lane<V>(acc[t], lane) + s_cbias[t];
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const float v = warp_sum(acc[t][e]);
-        if (lane == e) mine[t] = v;
-        acc[t][e] = 0.f;
-      }
+      for (int e = 0; e < V; ++e) acc[t][e] = 0.f;
     }
     const int o = r * V + lane;
     const bool writer = lane < V && o < p.O;
-    const T* bias = reinterpret_cast<const T*>(p.bias);
-    T* y = reinterpret_cast<T*>(p.y);
     if (pl.nch == 1) {
       if (writer) {
         const float bv = bias ? DT<T>::to_float(bias[o]) : 0.f;
 #pragma unroll
-        for (int t = 0; t < NT; ++t) y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(mine[t] + s_cbias[t] + bv);
+        for (int t = 0; t < NT; ++t) y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(mine[t] + bv);
+      }
+    } else if (pl.cluster) {
+      // DSMEM hand-off: slot [krow][chunk][t][e] of the leader's (rank 0) partial-sum table
+      if (lane < V) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t)
+          st_cluster_f32(part_leader + uint32_t(((krow * pl.nch + chunk) * NT + t) * V + lane) * 4u, mine[t]);
       }
     } else {
+      // global-memory variant: the last chunk of a row to arrive sums all chunks in order
       const int64_t opad = int64_t(p.Ro) * V;
       if (lane < V) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) p.partials[(int64_t(chunk) * NT + t) * opad + r * V + lane] = mine[t] + s_cbias[t];
+        for (int t = 0; t < NT; ++t) p.partials[(int64_t(chunk) * NT + t) * opad + r * V + lane] = mine[t];
         __threadfence();
       }
       __syncwarp();
       uint32_t prev = 0;
       if (lane == 0) prev = atomicAdd(&p.counters[r], 1u);
       prev = __shfl_sync(0xffffffffu, prev, 0);
-      if (prev == uint32_t(pl.nch - 1)) {  // last chunk of this row to arrive: sum in chunk order
+      if (prev == uint32_t(pl.nch - 1)) {
         __threadfence();
         if (writer) {
           const float bv = bias ? DT<T>::to_float(bias[o]) : 0.f;
@@ -344,7 +396,25 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
             y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(v + bv);
           }
         }
-        if (lane == 0) p.counters[r] = 0u;  // leave the workspace zeroed for the next launch
+        if (lane == 0) p.counters[r] = 0u;  // leave the counter region zeroed for the next launch
+      }
+    }
+  }
+
+  // -------- cluster epilogue: the leader sums the chunks in order and writes y ---------------
+  if (pl.cluster) {
+    cluster_arrive();  // release: this CTA's DSMEM stores are visible to the leader after its wait
+    cluster_wait();
+    if (chunk == 0) {
+      const int n = nrows_cta * NT * V;
+      for (int i = tid; i < n; i += blockDim.x) {
+        const int e = i % V, t = (i / V) % NT, krow = i / (V * NT);
+        const int o = (cta_in_chunk + pl.cpc * krow) * V + e;
+        if (o < p.O) {
+          float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
+          for (int ch = 0; ch < pl.nch; ++ch) v += s_part[((krow * pl.nch + ch) * NT + t) * V + e];
+          y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(v);
+        }
       }
     }
   }

@@ -56,7 +56,9 @@ struct GemvPlan {
   int res_rep;         // same for the residual codebook
   int nt;              // tokens per pass (1, 2 or 4)
   int sx_stride;       // floats per token row of x' in smem
-  uint32_t off_bars, off_cbias, off_pcol, off_wb, off_sx, off_res, off_main, off_ring;
+  int cluster;         // 1: the nch CTAs of a row set form a thread-block cluster (DSMEM split-K)
+  int ctas_per_sm;     // co-resident CTAs per SM the plan was sized for
+  uint32_t off_bars, off_cbias, off_pcol, off_wb, off_sx, off_part, off_res, off_main, off_ring;
   uint32_t stage_bytes;
   uint32_t smem_bytes;
   // workspace carve-up
