@@ -144,6 +144,26 @@ __device__ __forceinline__ float ldg_cg_f32(const float* p) {
   return r;
 }
 
+// 16-byte asynchronous global -> shared copy (LDGSTS): the gather does not occupy registers while it
+// is in flight, so the number of outstanding gathers per warp is bounded by shared memory only.
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, uint64_t policy) {
+  asm volatile("cp.async.ca.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t saddr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(saddr));
+  return r;
+}
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // programmatic dependent launch (PDL): no-ops unless the launch carries the attribute
 // ------------------------------------------------------------------------------------------
@@ -168,6 +188,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
 }
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+// remote shared-memory store whose completion is counted (in bytes) on an mbarrier of the SAME remote
+// CTA: the consumer just waits for the expected byte count -- no fence, no closing cluster barrier.
+__device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint32_t remote_bar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(remote_addr),
+               "r"(__float_as_uint(v)), "r"(remote_bar)
+               : "memory");
 }
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }

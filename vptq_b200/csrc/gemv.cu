@@ -1,9 +1,12 @@
 // Host side of the decode GEMV: work decomposition (GemvPlan), shared-memory carve-up, launch.
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <tuple>
 #include <unordered_set>
+#include <vector>
 
 #include "gemv_kernel.cuh"
 
@@ -12,16 +15,34 @@ namespace vptq_b200 {
 namespace {
 
 constexpr int kMaxChunkCols = 4096;      // bounds the x' slice in shared memory (16 KB per token)
-constexpr int kSegFields = 512;          // index fields per ring stage
 constexpr int kSmemReserve = 2048;       // head-room below the opt-in limit
-constexpr int kSmemPerSm = 233472;       // 228 KB per SM, 1 KB of it reserved per resident CTA
-constexpr int kMaxClusterPartBytes = 16384;
+constexpr int kMaxClusterPartBytes = 8192;
 
 bool supported_vec_len(int v) { return v == 2 || v == 4 || v == 6 || v == 8 || v == 10 || v == 12 || v == 16; }
 
 std::mutex g_mutex;
 std::unordered_set<const void*> g_attr_done;
 std::map<std::tuple<const void*, int, int, int>, int> g_max_clusters;
+
+// Developer tuning knobs (not part of the ABI): VPTQ_B200_GEMV_TUNE="nb=4,rep=1,stages=2,seg=512,warps=16,cpg=4"
+struct Tune {
+  int nb = 0, rep = -1, stages = 0, seg = 0, warps = 0, cpg = 0;
+};
+const Tune& tune() {
+  static Tune t = [] {
+    Tune r;
+    const char* e = std::getenv("VPTQ_B200_GEMV_TUNE");
+    if (!e) return r;
+    auto get = [&](const char* key, int& dst) {
+      const char* p = std::strstr(e, key);
+      if (p) dst = std::atoi(p + std::strlen(key));
+    };
+    get("nb=", r.nb), get("rep=", r.rep), get("stages=", r.stages), get("seg=", r.seg), get("warps=", r.warps),
+        get("cpg=", r.cpg);
+    return r;
+  }();
+  return t;
+}
 
 int ensure_smem_attr(const void* fn, int bytes) {
   std::lock_guard<std::mutex> lock(g_mutex);
@@ -78,6 +99,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
   const int S = (d.outlier_size > 0 && d.outlier_indices) ? d.outlier_size : 0;
   const int EB = 2 * v;
   const int sms = dev.sm_count;
+  const Tune& tn = tune();
   if (Ro > kMaxIndexRows) {
     set_error("gemv: %d index rows exceed the supported maximum %d", Ro, kMaxIndexRows);
     return VPTQ_ERR_UNSUPPORTED;
@@ -85,24 +107,26 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
 
   GemvPlan pl{};
   pl.nt = (v == 8) ? (tokens >= 4 ? 4 : (tokens >= 2 ? 2 : 1)) : 1;
-  pl.seg_fields = kSegFields;
+  pl.seg_fields = tn.seg ? tn.seg : 512;
   pl.stage_bytes = uint32_t(align_up(size_t(pl.seg_fields) * b / 8 + 16, 16));
+  pl.ctas_per_sm = 1;
 
   const size_t main_bytes = size_t(d.num_centroids) * EB;
   const size_t res_bytes = rb ? size_t(d.num_res_centroids) * EB : 0;
-  pl.res_rep = (rb && v == 8 && res_bytes * 8 <= 32768) ? 8 : 1;
   const bool main_fits = main_bytes <= 131072;
   const int main_rep_smem = (v == 8 && main_bytes * 8 <= 32768) ? 8 : 1;
+  const int res_rep_want = tn.rep >= 0 ? (tn.rep ? 8 : 1) : 8;
+  const int res_rep_max = (rb && v == 8 && res_bytes * 8 <= 32768) ? res_rep_want : 1;
+  const int smem_limit = dev.smem_optin - kSmemReserve;
+  const int slots = sms;  // one CTA per SM: the whole register file and shared memory feed one pipeline
 
-  // One attempt = (CTAs per SM, warps per CTA, main codebook in smem?).  First fit wins:
-  // two 8-warp CTAs per SM (prologue of one overlaps the main loop of the other, and of the
-  // previous kernel's tail under PDL), else one 16-warp CTA, shedding ring stages before that.
-  struct Attempt { int ctas_per_sm, warps; bool main_smem; };
-  const Attempt attempts[] = {{2, 8, true}, {1, 16, true}, {1, 8, true}, {2, 8, false}, {1, 16, false}, {1, 8, false}};
+  // One attempt = (warps per CTA, main codebook in shared memory?).  First fit wins.
+  struct Attempt { int warps; bool main_smem; };
+  const Attempt attempts[] = {{16, true}, {8, true}, {16, false}, {8, false}};
   for (const Attempt& a : attempts) {
     if (a.main_smem && !main_fits) continue;
-    const int slots = sms * a.ctas_per_sm;
-    const int smem_limit = a.ctas_per_sm == 1 ? dev.smem_optin - kSmemReserve : kSmemPerSm / 2 - 1024 - 512;
+    if (tn.warps && a.warps != tn.warps) continue;
+    const bool async = !a.main_smem && v == 8;
 
     // ---- column chunks: cpg per codebook group, width a multiple of 128 columns ----------------
     // cost ~ fields streamed by the busiest CTA + per-CTA prologue + per-row epilogue; chunk
@@ -110,6 +134,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
     int best_cpg = 0, best_cc = 0;
     double best_cost = 1e300;
     for (int cpg = 1; cpg <= 64; cpg *= 2) {
+      if (tn.cpg && cpg != tn.cpg) continue;
       const int cc = int(align_up(size_t((gs + cpg - 1) / cpg), 128));
       if (cc > kMaxChunkCols) continue;
       if (cpg > 1 && cc < 256) break;
@@ -120,6 +145,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
       const int rows_cta = (Ro + cpc - 1) / cpc;
       double cost = double(rows_cta) * cc + 600.0 + 0.35 * cc;
       cost += (nch <= 8 ? 24.0 : 96.0) * rows_cta;
+      cost *= 1.0 + 0.01 * ilog2(real_cpg);  // ties go to fewer, wider chunks
       if (rows_cta < a.warps / 2) cost *= 1.0 + 0.6 * (a.warps / 2 - rows_cta) / double(a.warps);
       if (cost < best_cost) best_cost = cost, best_cpg = real_cpg, best_cc = cc;
     }
@@ -131,19 +157,19 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
     if (pl.nch > slots) continue;
     pl.cpc = std::max(1, std::min(slots / pl.nch, Ro));
     const int rows_cta = (Ro + pl.cpc - 1) / pl.cpc;
-    // cluster reduce needs the leader to hold every row's chunk partials; allow for a smaller grid
-    // (cpc is clamped to the co-schedulable cluster count below) with 25% slack
+    // cluster reduce: the leader holds every row's chunk partials; cpc may still be clamped to the
+    // co-schedulable cluster count below, hence 25% slack
     const size_t part_bytes = size_t(rows_cta + rows_cta / 4 + 1) * pl.nch * pl.nt * v * 4;
     pl.cluster = (pl.nch >= 2 && pl.nch <= 8 && part_bytes <= kMaxClusterPartBytes) ? 1 : 0;
     pl.main_in_smem = a.main_smem ? 1 : 0;
     pl.main_rep = a.main_smem ? main_rep_smem : 1;
-    pl.ctas_per_sm = a.ctas_per_sm;
 
     // ---- shared memory carve-up ----------------------------------------------------------------
-    auto carve = [&](int warps, int stages) -> size_t {
+    auto carve = [&](int warps, int stages, int nb, int res_rep) -> size_t {
+      pl.res_rep = res_rep;
       size_t off = 0;
       pl.off_bars = uint32_t(off);
-      off += align_up(size_t(1 + warps * stages) * 8, 128);
+      off += align_up(size_t(2 + warps * stages) * 8, 128);
       pl.off_cbias = uint32_t(off);
       off += align_up(size_t(pl.nt) * (1 + warps) * 4, 128);
       const int n_all = pl.chunk_cols + S;
@@ -157,18 +183,37 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
       pl.off_part = uint32_t(off);
       if (pl.cluster) off += align_up(part_bytes, 128);
       pl.off_res = uint32_t(off);
-      off += align_up(res_bytes * pl.res_rep, 128);
+      off += align_up(res_bytes * res_rep, 128);
       pl.off_main = uint32_t(off);
       if (a.main_smem) off += align_up(main_bytes * pl.main_rep, 128);
+      pl.off_raw = uint32_t(off);
+      off += align_up((res_rep > 1 ? res_bytes : 0) + (a.main_smem && pl.main_rep > 1 ? main_bytes : 0), 128);
       pl.off_ring = uint32_t(off);
-      off += size_t(warps) * stages * pl.stage_bytes;
+      off += align_up(size_t(warps) * stages * pl.stage_bytes, 128);
+      pl.off_gbuf = uint32_t(off);
+      off += size_t(warps) * nb * kGatherBatch * 512;
       return off;
     };
+    // what to shed, in order, until the layout fits
+    struct Shape { int stages, nb, rep; };
+    std::vector<Shape> shapes;
+    if (async) {
+      // the gather ring (memory-level parallelism on the L2 tier) is worth more than the
+      // conflict-free residual table or a deeper index ring
+      for (int nb : {4, 3, 2})
+        for (int rep : {res_rep_max, 1})
+          for (int st : {3, 2}) shapes.push_back({st, nb, rep});
+    } else {
+      for (int st : {4, 3, 2})
+        for (int rep : {res_rep_max, 1}) shapes.push_back({st, 0, rep});
+    }
     bool placed = false;
-    for (int stages : {4, 3, 2}) {
-      const size_t need = carve(a.warps, stages);
+    for (const Shape& sh : shapes) {
+      if (tn.nb && async && sh.nb != tn.nb) continue;
+      if (tn.stages && sh.stages != tn.stages) continue;
+      const size_t need = carve(a.warps, sh.stages, sh.nb, sh.rep);
       if (need <= size_t(smem_limit)) {
-        pl.threads = a.warps * 32, pl.stages = stages, pl.smem_bytes = uint32_t(need);
+        pl.threads = a.warps * 32, pl.stages = sh.stages, pl.gstages = sh.nb, pl.smem_bytes = uint32_t(need);
         placed = true;
         break;
       }
@@ -183,7 +228,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
                        : -1;
       if (n > 0 && n < pl.cpc) pl.cpc = n;
       const int rows2 = (Ro + pl.cpc - 1) / pl.cpc;
-      if (size_t(rows2) * pl.nch * pl.nt * v * 4 > align_up(part_bytes, 128)) pl.cluster = 0;  // (never with 25% slack)
+      if (size_t(rows2) * pl.nch * pl.nt * v * 4 > align_up(part_bytes, 128)) pl.cluster = 0;
     }
     pl.grid = pl.nch * pl.cpc;
     pl.ws_counters_bytes = kCounterRegionBytes;

@@ -12,14 +12,17 @@
 //     of index rows; every warp owns whole rows and keeps the v partial sums in registers;
 //   * the packed index words of a row arrive through a per-warp ring of 1-D TMA bulk copies
 //     (cp.async.bulk + mbarrier, L2 evict_first);
-//   * codebooks are staged in shared memory (bank-group replicated when small, so 128-bit gathers
-//     are conflict-free) or, when they do not fit (65536 x 16 B = 1 MiB), gathered through L1/L2
-//     with an evict_last policy, 8 independent 16-byte gathers in flight per lane;
+//   * codebooks that fit are staged in shared memory by TMA (small ones bank-group replicated so
+//     that 128-bit gathers are conflict-free).  A 65536-entry codebook (1 MiB) cannot be: its
+//     16-byte entries are gathered from L2 with cp.async (LDGSTS) into a per-warp shared-memory
+//     ring, so a lane keeps 12 gathers in flight without holding them in registers -- the
+//     measured bound for this tier is one gather per clock per SM (L1TEX tag stage), and only
+//     deep memory-level parallelism gets near it;
 //   * the split-K reduction over column chunks runs inside a thread-block cluster: every CTA
-//     pushes its partial sums into the leader's shared memory (st.shared::cluster) and one
-//     cluster barrier later the leader sums them in chunk order and writes y.  No second kernel
-//     (the reference launches `sum(-1)`, csrc/quant_gemv.cu:235), no global atomics or fences.
-//     Layers cut into more than 8 chunks use a global-memory variant of the same scheme.
+//     pushes its per-row partial sums into the leader's shared memory with st.async, completion
+//     counted on an mbarrier there; the leader sums the chunks in order and writes y.  No second
+//     kernel (the reference launches `sum(-1)`, csrc/quant_gemv.cu:235), no global atomics or
+//     fences.  Layers cut into more than 8 chunks use a global-memory variant of the same scheme.
 #pragma once
 
 #include "common.cuh"
@@ -54,6 +57,8 @@ struct GemvParams {
   int idx_tma_ok;  // rows are 16-byte aligned -> bulk copies legal
   GemvPlan plan;
 };
+
+constexpr int kGatherBatch = 4;  // cp.async gathers per lane and batch (async path)
 
 // acc[e] += xv * (c[e] + r[e]) for one gathered (main, residual) entry pair, fp32 arithmetic
 template <typename T, int V, bool RES>
@@ -110,8 +115,10 @@ __device__ __forceinline__ float warp_reduce_to_lane(float (&acc)[V], int lane) 
 template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
 __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr int U = (NT == 1 && V <= 8) ? 8 : 4;  // independent codebook gathers in flight per lane
+  constexpr bool ASYNC = !MAIN_SMEM && V == 8;    // main codebook gathered from L2 by cp.async
+  constexpr int U = (NT == 1 && V <= 8) ? 8 : 4;  // register path: gathers in flight per lane
   constexpr int EB = 2 * V;                       // bytes per codebook entry
+  constexpr int GB = kGatherBatch, BF = 32 * GB;  // async path: gathers per lane / fields per batch
   const GemvPlan& pl = p.plan;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -133,28 +140,34 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   float* s_part = reinterpret_cast<float*>(smem + pl.off_part);
   uint8_t* s_res = smem + pl.off_res;
   uint8_t* s_main = smem + pl.off_main;
+  uint8_t* s_raw = smem + pl.off_raw;  // TMA landing zone of tables that are then replicated
   uint8_t* ring = smem + pl.off_ring + warp * pl.stages * pl.stage_bytes;
   uint64_t* cb_bar = &bars[0];
-  uint64_t* full = &bars[1 + warp * pl.stages];
+  uint64_t* part_bar = &bars[1];
+  uint64_t* full = &bars[2 + warp * pl.stages];
 
   const T* cent_g = reinterpret_cast<const T*>(p.centroids) + int64_t(g) * p.cb_stride;
   const T* res_g = RES ? reinterpret_cast<const T*>(p.res_centroids) + int64_t(g) * p.rcb_stride : nullptr;
 
+  const int nrows_cta = cta_in_chunk < p.Ro ? (p.Ro - cta_in_chunk + pl.cpc - 1) / pl.cpc : 0;
+
   // -------- barrier init -----------------------------------------------------------------
   if (tid == 0) {
     mbar_init(cb_bar, 1);
-    for (int i = 0; i < nwarps * pl.stages; ++i) mbar_init(&bars[1 + i], 1);
+    mbar_init(part_bar, 1);
+    for (int i = 0; i < nwarps * pl.stages; ++i) mbar_init(&bars[2 + i], 1);
     fence_mbar_init();
+    // leader: every chunk (this one included) delivers NT*V floats per row with st.async
+    if (pl.cluster && chunk == 0) mbar_arrive_expect_tx(part_bar, uint32_t(pl.nch * nrows_cta * NT * V) * 4u);
   }
   __syncthreads();
-  if (pl.cluster) cluster_arrive();  // phase 0: "this CTA is running" (waited before the first DSMEM store)
+  if (pl.cluster) cluster_arrive();  // "this CTA runs and its barriers exist"; waited before the first st.async
   pdl_launch_dependents();           // the next kernel may start its own weight-only prologue now
 
   const uint64_t pol_stream = policy_evict_first();
   const uint64_t pol_keep = policy_evict_last();
 
   // -------- work list of this warp -------------------------------------------------------
-  const int nrows_cta = cta_in_chunk < p.Ro ? (p.Ro - cta_in_chunk + pl.cpc - 1) / pl.cpc : 0;
   const int nunits = warp < nrows_cta ? (nrows_cta - warp + nwarps - 1) / nwarps : 0;
   const int nseg = (ncols + pl.seg_fields - 1) / pl.seg_fields;
   const int total = nunits * nseg;
@@ -189,21 +202,28 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   for (int q = 0; q < npre; ++q) issue(q);
 
   // -------- codebooks -> shared memory (weights only: legal before the PDL wait) -----------
-  // rep == 1: TMA bulk copies.  rep == 8: entry i is stored 8 times, copy k at 16-byte slot
-  // i*8+k, so that lane L reads slot i*8 + (L & 7): the 8 lanes of a quarter-warp always hit
-  // 8 different 16-byte bank groups -> conflict-free 128-bit gathers.
-  uint32_t cb_tx = 0;
-  auto stage_table = [&](uint8_t* dst, const T* src, int entries, int rep) {
+  // rep == 1: TMA bulk copy straight to its place.  rep == 8 (16-byte entries only): TMA into a
+  // landing zone, then entry i is stored 8 times, copy k at 16-byte slot i*8+k; lane L reads slot
+  // i*8 + (L & 7), so the 8 lanes of a quarter-warp always hit 8 different 16-byte bank groups
+  // and 128-bit gathers are conflict-free.
+  uint32_t cb_tx = 0, raw_off = 0;
+  uint32_t raw_res = 0, raw_main = 0;  // landing-zone offsets (valid when the table is replicated)
+  bool tma_res = false, tma_main = false;
+  auto stage_table = [&](uint8_t* dst, const T* src, int entries, int rep, uint32_t& raw_at, bool& by_tma) {
     const uint32_t bytes = uint32_t(entries) * EB;
-    if (rep == 1 && (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+    by_tma = (bytes & 15u) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (rep == 1 || V == 8);
+    if (by_tma) {
+      uint8_t* land = rep == 1 ? dst : s_raw + raw_off;
+      raw_at = raw_off;
+      if (rep > 1) raw_off += bytes;
       if (tid == 0) {
         for (uint32_t off = 0; off < bytes; off += 32768u) {
           const uint32_t n = min(32768u, bytes - off);
-          tma_bulk_g2s(dst + off, reinterpret_cast<const uint8_t*>(src) + off, n, cb_bar, pol_keep);
+          tma_bulk_g2s(land + off, reinterpret_cast<const uint8_t*>(src) + off, n, cb_bar, pol_keep);
         }
       }
       cb_tx += bytes;
-    } else {
+    } else {  // odd sizes / alignments: plain loads
       const uint32_t* s32 = reinterpret_cast<const uint32_t*>(src);
       uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
       constexpr int WPE = V / 2;  // words per entry
@@ -214,22 +234,51 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
       }
     }
   };
-  if constexpr (RES) stage_table(s_res, res_g, p.Kr, pl.res_rep);
-  if constexpr (MAIN_SMEM) stage_table(s_main, cent_g, p.K, pl.main_rep);
+  if constexpr (RES) stage_table(s_res, res_g, p.Kr, pl.res_rep, raw_res, tma_res);
+  if constexpr (MAIN_SMEM) stage_table(s_main, cent_g, p.K, pl.main_rep, raw_main, tma_main);
   if (tid == 0) {
     if (cb_tx) mbar_arrive_expect_tx(cb_bar, cb_tx);
     else mbar_arrive(cb_bar);
   }
 
   // -------- x' prologue, phase A: everything that does not depend on x --------------------
+  // four columns per thread and step, loads grouped by dependence level (perm -> scale, wbias)
   const T* scale = reinterpret_cast<const T*>(p.scale);
   const T* wbias = reinterpret_cast<const T*>(p.wbias);
-  for (int i = tid; i < n_all; i += blockDim.x) {
-    const int c = i < ncols ? p.S + g * p.gs + f0 + i : i - ncols;
-    const int pc = p.perm ? int(p.perm[c]) : c;
-    s_pcol[i] = uint16_t(pc);
-    sx[i] = scale ? DT<T>::to_float(scale[pc]) : 1.f;
-    s_wb[i] = wbias ? DT<T>::to_float(wbias[pc]) : 0.f;
+  for (int i0 = tid; i0 < n_all; i0 += 4 * blockDim.x) {
+    int pc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * blockDim.x;
+      const int c = i < ncols ? p.S + g * p.gs + f0 + i : i - ncols;
+      pc[k] = i < n_all ? (p.perm ? int(p.perm[c]) : c) : 0;
+    }
+    float sc[4], wb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      sc[k] = scale ? DT<T>::to_float(scale[pc[k]]) : 1.f;
+      wb[k] = wbias ? DT<T>::to_float(wbias[pc[k]]) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * blockDim.x;
+      if (i < n_all) s_pcol[i] = uint16_t(pc[k]), sx[i] = sc[k], s_wb[i] = wb[k];
+    }
+  }
+
+  // replicate TMA-landed tables (smem -> smem) once they have arrived
+  if constexpr (RES || MAIN_SMEM) mbar_wait(cb_bar, 0);
+  if constexpr (V == 8) {
+    auto replicate = [&](uint8_t* dst, uint32_t raw_at, int entries) {
+      const uint32_t src = smem_u32(s_raw + raw_at), d = smem_u32(dst);
+      for (int e = tid; e < entries; e += blockDim.x) {
+        const uint4 v = lds_v4(src + e * 16);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) sts_v4(d + (e * 8 + c) * 16, v);
+      }
+    };
+    if (RES && tma_res && pl.res_rep > 1) replicate(s_res, raw_res, p.Kr);
+    if (MAIN_SMEM && tma_main && pl.main_rep > 1) replicate(s_main, raw_main, p.K);
   }
 
   // -------- phase B: x arrives from the previous kernel ------------------------------------
@@ -239,14 +288,26 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     float bs[NT];
 #pragma unroll
     for (int t = 0; t < NT; ++t) bs[t] = 0.f;
-    for (int i = tid; i < n_all; i += blockDim.x) {
-      const int pc = s_pcol[i];
-      const float sc = sx[i], wb = s_wb[i];
+    for (int i0 = tid; i0 < n_all; i0 += 4 * blockDim.x) {
+      float xv[4][NT];
 #pragma unroll
-      for (int t = NT - 1; t >= 0; --t) {
-        const float xv = DT<T>::to_float(x[int64_t(t) * p.x_stride + pc]);
-        sx[t * pl.sx_stride + i] = xv * sc;
-        bs[t] = fmaf(xv, wb, bs[t]);
+      for (int k = 0; k < 4; ++k) {
+        const int i = min(i0 + k * int(blockDim.x), n_all - 1);
+        const int pc = s_pcol[i];
+#pragma unroll
+        for (int t = 0; t < NT; ++t) xv[k][t] = DT<T>::to_float(x[int64_t(t) * p.x_stride + pc]);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * blockDim.x;
+        if (i < n_all) {
+          const float sc = sx[i], wb = s_wb[i];
+#pragma unroll
+          for (int t = NT - 1; t >= 0; --t) {
+            sx[t * pl.sx_stride + i] = xv[k][t] * sc;
+            bs[t] = fmaf(xv[k][t], wb, bs[t]);
+          }
+        }
       }
     }
     // block-reduce the weight_bias term of this chunk: s_cbias[t] = sum_{c in chunk} x[perm c]*wbias[perm c]
@@ -264,8 +325,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     }
   }
   __syncthreads();
-  if constexpr (RES || MAIN_SMEM) mbar_wait(cb_bar, 0);
-  if (pl.cluster) cluster_wait();  // every CTA of the cluster has started: its smem may be written
+  if (pl.cluster) cluster_wait();  // every CTA of the cluster runs: the leader's smem may be written
 
   // -------- main loop ------------------------------------------------------------------------
   const uint32_t fmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
@@ -276,6 +336,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   const uint32_t s_res_lane = smem_u32(s_res) + (pl.res_rep > 1 ? (lane & 7) * EB : 0);
   const uint8_t* cent_bytes = reinterpret_cast<const uint8_t*>(cent_g);
   const uint32_t part_leader = pl.cluster ? mapa_shared(smem_u32(s_part), 0) : 0u;
+  const uint32_t bar_leader = pl.cluster ? mapa_shared(smem_u32(part_bar), 0) : 0u;
   const T* bias = reinterpret_cast<const T*>(p.bias);
   T* y = reinterpret_cast<T*>(p.y);
 
@@ -285,52 +346,17 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
 #pragma unroll
     for (int e = 0; e < V; ++e) acc[t][e] = 0.f;
 
-  for (int q = 0; q < total; ++q) {
-    const int u = q / nseg, s = q - u * nseg;
-    const int krow = warp + nwarps * u;  // position of the row in this CTA's row list
+  // field j of ring stage `sw` (0 for lanes past the end: they gather entry 0 and multiply by zero)
+  auto field_at = [&](const uint32_t* sw, int j, int nf) -> uint32_t {
+    const uint32_t bit = uint32_t(j) * uint32_t(b);
+    const uint32_t w = bit >> 5;
+    const uint32_t f = __funnelshift_r(sw[w], sw[w + 1], bit & 31u) & fmask;
+    return j < nf ? f : 0u;
+  };
+
+  // one row of this warp is complete: outlier columns, warp reduction, hand-off
+  auto finish_row = [&](int krow) {
     const int r = cta_in_chunk + pl.cpc * krow;
-    const int seg0 = s * pl.seg_fields;  // first field of the segment, relative to the chunk
-    const int nf = min(pl.seg_fields, ncols - seg0);
-    const int st = q % pl.stages;
-    mbar_wait(&full[st], uint32_t(q / pl.stages) & 1u);
-    const uint32_t* sw = reinterpret_cast<const uint32_t*>(ring + st * pl.stage_bytes);
-    const float* sxs = sx + seg0;
-
-    for (int jb = 0; jb < nf; jb += 32 * U) {
-      uint32_t fld[U];
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const int j = jb + 32 * k + lane;
-        const uint32_t bit = uint32_t(j) * uint32_t(b);
-        const uint32_t w = bit >> 5;
-        const uint32_t f = __funnelshift_r(sw[w], sw[w + 1], bit & 31u) & fmask;
-        fld[k] = j < nf ? f : 0u;  // out-of-range lanes gather entry 0 and multiply by zero
-      }
-      uint32_t cw[U][V / 2];
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const uint32_t mi = fld[k] & imask;
-        if constexpr (MAIN_SMEM) lds_entry<V>(cw[k], s_main_lane + mi * main_stride);
-        else ldg_entry<V>(cw[k], cent_bytes + size_t(mi) * EB, pol_keep);
-      }
-#pragma unroll
-      for (int k = 0; k < U; ++k) {
-        const int j = jb + 32 * k + lane;
-        uint32_t rw[V / 2];
-        if constexpr (RES) lds_entry<V>(rw, s_res_lane + (fld[k] >> p.ib) * res_stride);
-#pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const float xv = j < nf ? sxs[t * pl.sx_stride + j] : 0.f;
-          fma_entry<T, V, RES>(acc[t], xv, cw[k], rw);
-        }
-      }
-    }
-    __syncwarp();  // every lane's index words are in registers (its gathers depended on them)
-    if (q + pl.stages < total) issue(q + pl.stages);
-
-    if (s != nseg - 1) continue;
-
-    // ---- row finished: outlier columns (owned by chunk 0), reduction, hand-off -------------
     if (owns_outliers) {
       const T* ocb = reinterpret_cast<const T*>(p.outlier_cb);
       const float* sxo = sx + ncols;
@@ -371,7 +397,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
       if (lane < V) {
 #pragma unroll
         for (int t = 0; t < NT; ++t)
-          st_cluster_f32(part_leader + uint32_t(((krow * pl.nch + chunk) * NT + t) * V + lane) * 4u, mine[t]);
+          st_async_f32(part_leader + uint32_t(((krow * pl.nch + chunk) * NT + t) * V + lane) * 4u, mine[t], bar_leader);
       }
     } else {
       // global-memory variant: the last chunk of a row to arrive sums all chunks in order
@@ -399,22 +425,126 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
         if (lane == 0) p.counters[r] = 0u;  // leave the counter region zeroed for the next launch
       }
     }
+  };
+
+  if constexpr (ASYNC) {
+    // ---- L2-resident main codebook: cp.async gathers through a per-warp shared-memory ring -------
+    // Batches of BF = 128 fields (GB = 4 per lane).  Batch bi is ISSUED (indices extracted, 4
+    // cp.async per lane, one commit group) NB-1 batches before it is CONSUMED (wait_group, own-slot
+    // LDS.128, residual LDS.128, fp32 FMAs), so each lane has up to 4*(NB-1) gathers in flight.
+    const int NB = pl.gstages;
+    const int bpu = (ncols + BF - 1) / BF;     // batches per unit (row x chunk)
+    const int seg_b = pl.seg_fields / BF;      // batches per ring segment
+    const int nb_total = nunits * bpu;
+    const uint32_t gbuf = smem_u32(smem + pl.off_gbuf) + uint32_t(warp) * uint32_t(NB * GB * 512) + lane * 16;
+
+    auto issue_batch = [&](int bi) {
+      const int u = bi / bpu, bl = bi - u * bpu;
+      const int s = bl / seg_b, off = (bl - s * seg_b) * BF;
+      const int q = u * nseg + s, st = q % pl.stages;
+      if (off == 0) mbar_wait(&full[st], uint32_t(q / pl.stages) & 1u);  // first touch of the segment
+      const int nf = min(pl.seg_fields, ncols - s * pl.seg_fields);
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(ring + st * pl.stage_bytes);
+      const uint32_t slot = gbuf + uint32_t((bi % NB) * GB) * 512u;
+#pragma unroll
+      for (int k = 0; k < GB; ++k) {
+        const uint32_t mi = field_at(sw, off + 32 * k + lane, nf) & imask;
+        cp_async_16(slot + k * 512, cent_bytes + size_t(mi) * EB, pol_keep);
+      }
+    };
+
+    for (int bi = 0; bi < NB - 1; ++bi) {  // always NB-1 groups, empty ones included (see wait below)
+      if (bi < nb_total) issue_batch(bi);
+      cp_async_commit();
+    }
+    for (int bi = 0; bi < nb_total; ++bi) {
+      if (bi + NB - 1 < nb_total) issue_batch(bi + NB - 1);
+      cp_async_commit();  // (possibly empty) keeps "group of batch bi" = NB-1 groups back
+      // wait until at most NB-1 groups are pending -> batch bi has landed (own slots only: no sync)
+      switch (NB) {
+        case 2: cp_async_wait<1>(); break;
+        case 3: cp_async_wait<2>(); break;
+        default: cp_async_wait<3>(); break;
+      }
+      const int u = bi / bpu, bl = bi - u * bpu;
+      const int s = bl / seg_b, off = (bl - s * seg_b) * BF;
+      const int q = u * nseg + s, st = q % pl.stages;
+      const int seg0 = s * pl.seg_fields;
+      const int nf = min(pl.seg_fields, ncols - seg0);
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(ring + st * pl.stage_bytes);
+      const uint32_t slot = gbuf + uint32_t((bi % NB) * GB) * 512u;
+      const float* sxs = sx + seg0;
+#pragma unroll
+      for (int k = 0; k < GB; ++k) {
+        const int j = off + 32 * k + lane;
+        const uint32_t f = field_at(sw, j, nf);
+        uint32_t cw[V / 2], rw[V / 2];
+        lds_entry<V>(cw, slot + k * 512);
+        if constexpr (RES) lds_entry<V>(rw, s_res_lane + (f >> p.ib) * res_stride);
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const float xv = j < nf ? sxs[t * pl.sx_stride + j] : 0.f;
+          fma_entry<T, V, RES>(acc[t], xv, cw, rw);
+        }
+      }
+      const bool seg_done = off + BF >= nf;
+      if (seg_done) {
+        __syncwarp();  // all lanes are past their last read of this ring stage
+        if (q + pl.stages < total) issue(q + pl.stages);
+        if (s == nseg - 1) finish_row(warp + nwarps * u);
+      }
+    }
+  } else {
+    // ---- register path: codebook in shared memory (or V != 8): U gathers per lane in flight -------
+    for (int q = 0; q < total; ++q) {
+      const int u = q / nseg, s = q - u * nseg;
+      const int seg0 = s * pl.seg_fields;  // first field of the segment, relative to the chunk
+      const int nf = min(pl.seg_fields, ncols - seg0);
+      const int st = q % pl.stages;
+      mbar_wait(&full[st], uint32_t(q / pl.stages) & 1u);
+      const uint32_t* sw = reinterpret_cast<const uint32_t*>(ring + st * pl.stage_bytes);
+      const float* sxs = sx + seg0;
+
+      for (int jb = 0; jb < nf; jb += 32 * U) {
+        uint32_t fld[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) fld[k] = field_at(sw, jb + 32 * k + lane, nf);
+        uint32_t cw[U][V / 2];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const uint32_t mi = fld[k] & imask;
+          if constexpr (MAIN_SMEM) lds_entry<V>(cw[k], s_main_lane + mi * main_stride);
+          else ldg_entry<V>(cw[k], cent_bytes + size_t(mi) * EB, pol_keep);
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int j = jb + 32 * k + lane;
+          uint32_t rw[V / 2];
+          if constexpr (RES) lds_entry<V>(rw, s_res_lane + (fld[k] >> p.ib) * res_stride);
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            const float xv = j < nf ? sxs[t * pl.sx_stride + j] : 0.f;
+            fma_entry<T, V, RES>(acc[t], xv, cw[k], rw);
+          }
+        }
+      }
+      __syncwarp();  // every lane's index words are in registers (its gathers depended on them)
+      if (q + pl.stages < total) issue(q + pl.stages);
+      if (s == nseg - 1) finish_row(warp + nwarps * u);
+    }
   }
 
   // -------- cluster epilogue: the leader sums the chunks in order and writes y ---------------
-  if (pl.cluster) {
-    cluster_arrive();  // release: this CTA's DSMEM stores are visible to the leader after its wait
-    cluster_wait();
-    if (chunk == 0) {
-      const int n = nrows_cta * NT * V;
-      for (int i = tid; i < n; i += blockDim.x) {
-        const int e = i % V, t = (i / V) % NT, krow = i / (V * NT);
-        const int o = (cta_in_chunk + pl.cpc * krow) * V + e;
-        if (o < p.O) {
-          float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
-          for (int ch = 0; ch < pl.nch; ++ch) v += s_part[((krow * pl.nch + ch) * NT + t) * V + e];
-          y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(v);
-        }
+  if (pl.cluster && chunk == 0) {
+    mbar_wait(part_bar, 0);  // all nch * nrows_cta * NT * V partial sums have landed
+    const int n = nrows_cta * NT * V;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const int e = i % V, t = (i / V) % NT, krow = i / (V * NT);
+      const int o = (cta_in_chunk + pl.cpc * krow) * V + e;
+      if (o < p.O) {
+        float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
+        for (int ch = 0; ch < pl.nch; ++ch) v += s_part[((krow * pl.nch + ch) * NT + t) * V + e];
+        y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(v);
       }
     }
   }
