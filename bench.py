@@ -117,7 +117,8 @@ def build_stack(m, q, device, rank, world, dtype):
                 # std 1/sqrt(in): unit gain, so activations stay O(1) through 224 chained layers
                 centroids=(torch.randn(1, K * v, device=device, generator=g) / i ** 0.5).to(dtype),
                 res_centroids=(0.25 * torch.randn(1, Kr * v, device=device, generator=g) / i ** 0.5).to(dtype),
-                perm=torch.randperm(i, device=device, generator=g).to(torch.int32).to(torch.uint16).view(torch.int16),
+                # uint16 payload behind an int16 view: int64 -> int16 narrowing keeps the low 16 bits
+                perm=torch.randperm(i, device=device, generator=g).to(torch.int16),
                 weight_scale=(1 + 0.1 * torch.randn(i, device=device, generator=g)).to(dtype),
                 weight_bias=(0.01 * torch.randn(i, device=device, generator=g) / i ** 0.5).to(dtype))
             t["desc"] = native.make_desc(
@@ -126,6 +127,9 @@ def build_stack(m, q, device, rank, world, dtype):
                 indices=t["indices"], centroids=t["centroids"], res_centroids=t["res_centroids"], outlier_indices=None,
                 outlier_centroids=None, perm=t["perm"], weight_scale=t["weight_scale"], weight_bias=t["weight_bias"],
                 bias=None)
+            if os.environ.get("BENCH_DEBUG"):
+                pv = t["perm"].view(torch.uint16).to(torch.int64)
+                assert int(pv.max()) == i - 1 and int(pv.min()) == 0 and pv.unique().numel() == i, "bad perm"
             t["in"], t["out"], t["out_loc"] = i, o, o_loc
             layer[name] = t
         stack.append(layer)
@@ -145,9 +149,13 @@ def make_step(m, stack, device, dtype, rank, world, flags):
     hs = [torch.zeros(1, h, device=device, dtype=dtype) for _ in range(2)]
     launches = [0]
 
+    debug_sync = bool(os.environ.get("BENCH_DEBUG"))
+
     def linear(t, x, y):
         if world == 1:
             native.quant_gemv(t["desc"], x, y, flags=flags)
+            if debug_sync and not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream().synchronize()
         else:
             # this rank owns rows [rank*o_loc, (rank+1)*o_loc); y is full width and zero elsewhere,
             # one all-reduce(sum) over NVLink per layer completes it (north_star)
@@ -191,7 +199,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=device)
     native.lib()
     dtype = torch.float16
-    m, q = LLAMA3_8B, QUANT
+    m, q = dict(LLAMA3_8B), QUANT
+    if args.debug_layers:
+        m["layers"] = args.debug_layers
     flags = 0 if args.no_pdl else native.FLAG_PDL
 
     stack = build_stack(m, q, device, rank, world, dtype)
@@ -365,6 +375,7 @@ def main():
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--debug-layers", type=int, default=0, help="debugging only: truncate the model (invalid as a result)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

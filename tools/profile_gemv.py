@@ -34,7 +34,7 @@ for cname in only:
         t = dict(indices=torch.randint(-2 ** 31, 2 ** 31 - 1, (1, ro, wd), device=dev, dtype=torch.int32, generator=g),
                  centroids=(torch.randn(1, K * v, device=dev, generator=g) / i ** 0.5).half(),
                  res=(torch.randn(1, max(Kr, 1) * v, device=dev, generator=g) / i ** 0.5).half() if Kr > 0 else None,
-                 perm=torch.randperm(i, device=dev, generator=g).to(torch.int32).to(torch.uint16).view(torch.int16),
+                 perm=torch.randperm(i, device=dev, generator=g).to(torch.int16),
                  ws=(1 + 0.1 * torch.randn(i, device=dev, generator=g)).half(),
                  wb=(0.01 * torch.randn(i, device=dev, generator=g)).half())
         desc = native.make_desc(dtype=torch.float16, in_features=i, out_features=o, vector_len=v, num_centroids=K,

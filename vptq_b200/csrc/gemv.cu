@@ -26,7 +26,7 @@ std::map<std::tuple<const void*, int, int, int>, int> g_max_clusters;
 
 // Developer tuning knobs (not part of the ABI): VPTQ_B200_GEMV_TUNE="nb=4,rep=1,stages=2,seg=512,warps=16,cpg=4"
 struct Tune {
-  int nb = 0, rep = -1, stages = 0, seg = 0, warps = 0, cpg = 0;
+  int nb = 0, rep = -1, stages = 0, seg = 0, warps = 0, cpg = 0, cluster = -1, async = -1;
 };
 const Tune& tune() {
   static Tune t = [] {
@@ -38,7 +38,7 @@ const Tune& tune() {
       if (p) dst = std::atoi(p + std::strlen(key));
     };
     get("nb=", r.nb), get("rep=", r.rep), get("stages=", r.stages), get("seg=", r.seg), get("warps=", r.warps),
-        get("cpg=", r.cpg);
+        get("cpg=", r.cpg), get("cluster=", r.cluster), get("async=", r.async);
     return r;
   }();
   return t;
@@ -126,7 +126,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
   for (const Attempt& a : attempts) {
     if (a.main_smem && !main_fits) continue;
     if (tn.warps && a.warps != tn.warps) continue;
-    const bool async = !a.main_smem && v == 8;
+    const bool async = !a.main_smem && v == 8 && tn.async != 0;
 
     // ---- column chunks: cpg per codebook group, width a multiple of 128 columns ----------------
     // cost ~ fields streamed by the busiest CTA + per-CTA prologue + per-row epilogue; chunk
@@ -160,7 +160,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
     // cluster reduce: the leader holds every row's chunk partials; cpc may still be clamped to the
     // co-schedulable cluster count below, hence 25% slack
     const size_t part_bytes = size_t(rows_cta + rows_cta / 4 + 1) * pl.nch * pl.nt * v * 4;
-    pl.cluster = (pl.nch >= 2 && pl.nch <= 8 && part_bytes <= kMaxClusterPartBytes) ? 1 : 0;
+    pl.cluster = (pl.nch >= 2 && pl.nch <= 8 && part_bytes <= kMaxClusterPartBytes && tn.cluster != 0) ? 1 : 0;
     pl.main_in_smem = a.main_smem ? 1 : 0;
     pl.main_rep = a.main_smem ? main_rep_smem : 1;
 

@@ -115,7 +115,7 @@ __device__ __forceinline__ float warp_reduce_to_lane(float (&acc)[V], int lane) 
 template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
 __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr bool ASYNC = !MAIN_SMEM && V == 8;    // main codebook gathered from L2 by cp.async
+  constexpr bool ASYNC = !MAIN_SMEM && V == 8;    // main codebook may be gathered from L2 by cp.async
   constexpr int U = (NT == 1 && V <= 8) ? 8 : 4;  // register path: gathers in flight per lane
   constexpr int EB = 2 * V;                       // bytes per codebook entry
   constexpr int GB = kGatherBatch, BF = 32 * GB;  // async path: gathers per lane / fields per batch
@@ -292,8 +292,8 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
       float xv[4][NT];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int i = min(i0 + k * int(blockDim.x), n_all - 1);
-        const int pc = s_pcol[i];
+        const int i = i0 + k * int(blockDim.x);
+        const int pc = i < n_all ? int(s_pcol[i]) : 0;  // own slots only: no barrier since phase A
 #pragma unroll
         for (int t = 0; t < NT; ++t) xv[k][t] = DT<T>::to_float(x[int64_t(t) * p.x_stride + pc]);
       }
@@ -427,7 +427,9 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     }
   };
 
-  if constexpr (ASYNC) {
+  bool use_async = false;
+  if constexpr (ASYNC) use_async = pl.gstages > 0;  // the plan falls back to registers when smem is short
+  if (use_async) {
     // ---- L2-resident main codebook: cp.async gathers through a per-warp shared-memory ring -------
     // Batches of BF = 128 fields (GB = 4 per lane).  Batch bi is ISSUED (indices extracted, 4
     // cp.async per lane, one commit group) NB-1 batches before it is CONSUMED (wait_group, own-slot
