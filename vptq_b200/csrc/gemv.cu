@@ -126,7 +126,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
   for (const Attempt& a : attempts) {
     if (a.main_smem && !main_fits) continue;
     if (tn.warps && a.warps != tn.warps) continue;
-    const bool async = !a.main_smem && v == 8 && tn.async != 0;
+    const bool async = false;
 
     // ---- column chunks: cpg per codebook group, width a multiple of 128 columns ----------------
     // cost ~ fields streamed by the busiest CTA + per-CTA prologue + per-row epilogue; chunk
@@ -190,8 +190,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
       off += align_up((res_rep > 1 ? res_bytes : 0) + (a.main_smem && pl.main_rep > 1 ? main_bytes : 0), 128);
       pl.off_ring = uint32_t(off);
       off += align_up(size_t(warps) * stages * pl.stage_bytes, 128);
-      pl.off_gbuf = uint32_t(off);
-      off += size_t(warps) * nb * kGatherBatch * 512;
+      (void)nb;
       return off;
     };
     // what to shed, in order, until the layout fits

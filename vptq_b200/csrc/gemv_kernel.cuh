@@ -14,10 +14,10 @@
 //     (cp.async.bulk + mbarrier, L2 evict_first);
 //   * codebooks that fit are staged in shared memory by TMA (small ones bank-group replicated so
 //     that 128-bit gathers are conflict-free).  A 65536-entry codebook (1 MiB) cannot be: its
-//     16-byte entries are gathered from L2 with cp.async (LDGSTS) into a per-warp shared-memory
-//     ring, so a lane keeps 12 gathers in flight without holding them in registers -- the
-//     measured bound for this tier is one gather per clock per SM (L1TEX tag stage), and only
-//     deep memory-level parallelism gets near it;
+//     16-byte entries are gathered through L1/L2 (evict_last), 8 independent gathers in flight
+//     per lane.  The measured bound of that tier is ~1.1 gathers per clock per SM (L1TEX tag
+//     stage, tools/gather_microbench.cu); a cp.async/LDGSTS gather ring was tried and measured
+//     slower (double index decode + shared-memory round trip), see DESIGN.md;
 //   * the split-K reduction over column chunks runs inside a thread-block cluster: every CTA
 //     pushes its per-row partial sums into the leader's shared memory with st.async, completion
 //     counted on an mbarrier there; the leader sums the chunks in order and writes y.  No second
@@ -57,8 +57,6 @@ struct GemvParams {
   int idx_tma_ok;  // rows are 16-byte aligned -> bulk copies legal
   GemvPlan plan;
 };
-
-constexpr int kGatherBatch = 4;  // cp.async gathers per lane and batch (async path)
 
 // acc[e] += xv * (c[e] + r[e]) for one gathered (main, residual) entry pair, fp32 arithmetic
 template <typename T, int V, bool RES>
@@ -115,10 +113,8 @@ __device__ __forceinline__ float warp_reduce_to_lane(float (&acc)[V], int lane) 
 template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
 __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  constexpr bool ASYNC = !MAIN_SMEM && V == 8;    // main codebook may be gathered from L2 by cp.async
-  constexpr int U = (NT == 1 && V <= 8) ? 8 : 4;  // register path: gathers in flight per lane
+  constexpr int U = (NT == 1 && V <= 8) ? 8 : 4;  // independent codebook gathers in flight per lane
   constexpr int EB = 2 * V;                       // bytes per codebook entry
-  constexpr int GB = kGatherBatch, BF = 32 * GB;  // async path: gathers per lane / fields per batch
   const GemvPlan& pl = p.plan;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -427,112 +423,69 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     }
   };
 
-  bool use_async = false;
-  if constexpr (ASYNC) use_async = pl.gstages > 0;  // the plan falls back to registers when smem is short
-  if (use_async) {
-    // ---- L2-resident main codebook: cp.async gathers through a per-warp shared-memory ring -------
-    // Batches of BF = 128 fields (GB = 4 per lane).  Batch bi is ISSUED (indices extracted, 4
-    // cp.async per lane, one commit group) NB-1 batches before it is CONSUMED (wait_group, own-slot
-    // LDS.128, residual LDS.128, fp32 FMAs), so each lane has up to 4*(NB-1) gathers in flight.
-    const int NB = pl.gstages;
-    const int bpu = (ncols + BF - 1) / BF;     // batches per unit (row x chunk)
-    const int seg_b = pl.seg_fields / BF;      // batches per ring segment
-    const int nb_total = nunits * bpu;
-    const uint32_t gbuf = smem_u32(smem + pl.off_gbuf) + uint32_t(warp) * uint32_t(NB * GB * 512) + lane * 16;
-
-    auto issue_batch = [&](int bi) {
-      const int u = bi / bpu, bl = bi - u * bpu;
-      const int s = bl / seg_b, off = (bl - s * seg_b) * BF;
-      const int q = u * nseg + s, st = q % pl.stages;
-      if (off == 0) mbar_wait(&full[st], uint32_t(q / pl.stages) & 1u);  // first touch of the segment
-      const int nf = min(pl.seg_fields, ncols - s * pl.seg_fields);
-      const uint32_t* sw = reinterpret_cast<const uint32_t*>(ring + st * pl.stage_bytes);
-      const uint32_t slot = gbuf + uint32_t((bi % NB) * GB) * 512u;
-#pragma unroll
-      for (int k = 0; k < GB; ++k) {
-        const uint32_t mi = field_at(sw, off + 32 * k + lane, nf) & imask;
-        cp_async_16(slot + k * 512, cent_bytes + size_t(mi) * EB, pol_keep);
+  {
+    // ---- rolling gather pipeline ---------------------------------------------------------------
+    // The warp walks its work list in groups of 32 fields (one per lane).  U register slots hold
+    // the main-codebook entries of U consecutive groups: as soon as slot k has been consumed
+    // (residual gather, fp32 FMAs) the gather of group n+U is issued into it, so a lane has U-1..U
+    // independent gathers in flight at all times, across segment and row boundaries.  Segment and
+    // row boundaries always fall between U-blocks (rows are padded to whole blocks).
+    const int gps = pl.seg_fields >> 5;                 // groups per ring segment (multiple of U)
+    const int ngu = ((ncols + 32 * U - 1) / (32 * U)) * U;  // groups per unit, padded to whole U-blocks
+    const int NG = nunits * ngu;                        // (padding groups decode to field 0, x' = 0)
+    uint32_t fld[U];
+    uint32_t cw[U][V / 2];
+    // load side: position of the next group to fetch
+    int l_gl = 0, l_st = 0, l_nf = 0;
+    uint32_t l_par = 0;
+    const uint32_t* l_sw = reinterpret_cast<const uint32_t*>(ring);
+    auto load = [&](uint32_t& f_out, uint32_t (&c_out)[V / 2]) {
+      const int gs_ = l_gl & (gps - 1);
+      if (gs_ == 0) {  // first group of a ring segment: wait for its TMA, once
+        mbar_wait(&full[l_st], l_par);
+        l_sw = reinterpret_cast<const uint32_t*>(ring + l_st * pl.stage_bytes);
+        l_nf = min(pl.seg_fields, ncols - (l_gl / gps) * pl.seg_fields);
+      }
+      const uint32_t f = field_at(l_sw, gs_ * 32 + lane, l_nf);
+      f_out = f;
+      const uint32_t mi = f & imask;
+      if constexpr (MAIN_SMEM) lds_entry<V>(c_out, s_main_lane + mi * main_stride);
+      else ldg_entry<V>(c_out, cent_bytes + size_t(mi) * EB, pol_keep);
+      ++l_gl;
+      if (l_gl == ngu || (l_gl & (gps - 1)) == 0) {  // next group starts a new segment (and maybe a new row)
+        if (++l_st == pl.stages) l_st = 0, l_par ^= 1u;
+        if (l_gl == ngu) l_gl = 0;
       }
     };
-
-    for (int bi = 0; bi < NB - 1; ++bi) {  // always NB-1 groups, empty ones included (see wait below)
-      if (bi < nb_total) issue_batch(bi);
-      cp_async_commit();
-    }
-    for (int bi = 0; bi < nb_total; ++bi) {
-      if (bi + NB - 1 < nb_total) issue_batch(bi + NB - 1);
-      cp_async_commit();  // (possibly empty) keeps "group of batch bi" = NB-1 groups back
-      // wait until at most NB-1 groups are pending -> batch bi has landed (own slots only: no sync)
-      switch (NB) {
-        case 2: cp_async_wait<1>(); break;
-        case 3: cp_async_wait<2>(); break;
-        default: cp_async_wait<3>(); break;
-      }
-      const int u = bi / bpu, bl = bi - u * bpu;
-      const int s = bl / seg_b, off = (bl - s * seg_b) * BF;
-      const int q = u * nseg + s, st = q % pl.stages;
-      const int seg0 = s * pl.seg_fields;
-      const int nf = min(pl.seg_fields, ncols - seg0);
-      const uint32_t* sw = reinterpret_cast<const uint32_t*>(ring + st * pl.stage_bytes);
-      const uint32_t slot = gbuf + uint32_t((bi % NB) * GB) * 512u;
-      const float* sxs = sx + seg0;
+    // consume side: groups done in the current unit, current unit, current flat segment
+    int c_gl = 0, c_u = 0, c_q = 0;
 #pragma unroll
-      for (int k = 0; k < GB; ++k) {
-        const int j = off + 32 * k + lane;
-        const uint32_t f = field_at(sw, j, nf);
-        uint32_t cw[V / 2], rw[V / 2];
-        lds_entry<V>(cw, slot + k * 512);
-        if constexpr (RES) lds_entry<V>(rw, s_res_lane + (f >> p.ib) * res_stride);
+    for (int k = 0; k < U; ++k)
+      if (k < NG) load(fld[k], cw[k]);
+    for (int n0 = 0; n0 < NG; n0 += U) {
+#pragma unroll
+      for (int k = 0; k < U; ++k) {
+        const int j = (c_gl + k) * 32 + lane;  // column of this lane's field, relative to the chunk
+        uint32_t rw[V / 2];
+        if constexpr (RES) lds_entry<V>(rw, s_res_lane + (fld[k] >> p.ib) * res_stride);
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const float xv = j < nf ? sxs[t * pl.sx_stride + j] : 0.f;
-          fma_entry<T, V, RES>(acc[t], xv, cw, rw);
+          const float xv = j < ncols ? sx[t * pl.sx_stride + j] : 0.f;
+          fma_entry<T, V, RES>(acc[t], xv, cw[k], rw);
+        }
+        if (n0 + k + U < NG) load(fld[k], cw[k]);  // refill the slot: group n0+k+U
+      }
+      c_gl += U;
+      const bool unit_done = c_gl == ngu;
+      if (unit_done || (c_gl & (gps - 1)) == 0) {  // a ring segment has been consumed
+        __syncwarp();  // every lane extracted all of its fields (extraction precedes consumption)
+        if (c_q + pl.stages < total) issue(c_q + pl.stages);
+        ++c_q;
+        if (unit_done) {
+          finish_row(warp + nwarps * c_u);
+          c_gl = 0, ++c_u;
         }
       }
-      const bool seg_done = off + BF >= nf;
-      if (seg_done) {
-        __syncwarp();  // all lanes are past their last read of this ring stage
-        if (q + pl.stages < total) issue(q + pl.stages);
-        if (s == nseg - 1) finish_row(warp + nwarps * u);
-      }
-    }
-  } else {
-    // ---- register path: codebook in shared memory (or V != 8): U gathers per lane in flight -------
-    for (int q = 0; q < total; ++q) {
-      const int u = q / nseg, s = q - u * nseg;
-      const int seg0 = s * pl.seg_fields;  // first field of the segment, relative to the chunk
-      const int nf = min(pl.seg_fields, ncols - seg0);
-      const int st = q % pl.stages;
-      mbar_wait(&full[st], uint32_t(q / pl.stages) & 1u);
-      const uint32_t* sw = reinterpret_cast<const uint32_t*>(ring + st * pl.stage_bytes);
-      const float* sxs = sx + seg0;
-
-      for (int jb = 0; jb < nf; jb += 32 * U) {
-        uint32_t fld[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k) fld[k] = field_at(sw, jb + 32 * k + lane, nf);
-        uint32_t cw[U][V / 2];
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-          const uint32_t mi = fld[k] & imask;
-          if constexpr (MAIN_SMEM) lds_entry<V>(cw[k], s_main_lane + mi * main_stride);
-          else ldg_entry<V>(cw[k], cent_bytes + size_t(mi) * EB, pol_keep);
-        }
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-          const int j = jb + 32 * k + lane;
-          uint32_t rw[V / 2];
-          if constexpr (RES) lds_entry<V>(rw, s_res_lane + (fld[k] >> p.ib) * res_stride);
-#pragma unroll
-          for (int t = 0; t < NT; ++t) {
-            const float xv = j < nf ? sxs[t * pl.sx_stride + j] : 0.f;
-            fma_entry<T, V, RES>(acc[t], xv, cw[k], rw);
-          }
-        }
-      }
-      __syncwarp();  // every lane's index words are in registers (its gathers depended on them)
-      if (q + pl.stages < total) issue(q + pl.stages);
-      if (s == nseg - 1) finish_row(warp + nwarps * u);
     }
   }
 
