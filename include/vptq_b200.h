@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define VPTQ_B200_ABI_VERSION 1
+#define VPTQ_B200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define VPTQ_B200_API __attribute__((visibility("default")))
@@ -110,6 +110,12 @@ typedef struct vptq_linear_desc {
   const void* weight_scale; /* [I] or NULL; scale and bias are both present or both NULL */
   const void* weight_bias;  /* [I] or NULL */
   const void* bias;         /* [O] or NULL */
+
+  /* Optional load-time derivatives (NULL = not provided; results are identical either way):
+     weight_scale / weight_bias gathered into QUANTISED column order, i.e. element c holds
+     weight_scale[perm[c]] -- lets the decode kernel load them without waiting for perm. */
+  const void* weight_scale_q; /* [I] or NULL */
+  const void* weight_bias_q;  /* [I] or NULL */
 } vptq_linear_desc;
 
 typedef enum vptq_op {

@@ -117,6 +117,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
       : "memory");
 }
 
+// asynchronous prefetch of [p, p + bytes) into L2 (bytes % 16 == 0, p 16-byte aligned)
+__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // global loads
 // ------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ std::map<std::tuple<const void*, int, int, int>, int> g_max_clusters;
 
 // Developer tuning knobs (not part of the ABI): VPTQ_B200_GEMV_TUNE="nb=4,rep=1,stages=2,seg=512,warps=16,cpg=4"
 struct Tune {
-  int nb = 0, rep = -1, stages = 0, seg = 0, warps = 0, cpg = 0, cluster = -1, async = -1;
+  int nb = 0, rep = -1, stages = 0, seg = 0, warps = 0, cpg = 0, cluster = -1, wsplit = 0;
 };
 const Tune& tune() {
   static Tune t = [] {
@@ -38,7 +38,7 @@ const Tune& tune() {
       if (p) dst = std::atoi(p + std::strlen(key));
     };
     get("nb=", r.nb), get("rep=", r.rep), get("stages=", r.stages), get("seg=", r.seg), get("warps=", r.warps),
-        get("cpg=", r.cpg), get("cluster=", r.cluster), get("async=", r.async);
+        get("cpg=", r.cpg), get("cluster=", r.cluster), get("wsplit=", r.wsplit);
     return r;
   }();
   return t;
@@ -128,10 +128,13 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
     if (tn.warps && a.warps != tn.warps) continue;
     const bool async = false;
 
-    // ---- column chunks: cpg per codebook group, width a multiple of 128 columns ----------------
-    // cost ~ fields streamed by the busiest CTA + per-CTA prologue + per-row epilogue; chunk
-    // counts up to 8 reduce through the cluster, more than 8 through global memory (dearer).
-    int best_cpg = 0, best_cc = 0;
+    // ---- column chunks (cpg per codebook group, multiples of 128 columns) x warps per row -------
+    // A CTA streams rows_cta * cc fields; its nwarps/wsplit row slots work in parallel, each row
+    // cut over wsplit warps.  Chunk counts up to 8 reduce through a cluster (the co-schedulable
+    // cluster count can leave SMs idle: 4-CTA clusters fill only 132 of 148 SMs), more than 8
+    // through global memory.
+    GemvKernelFn fn_probe = pick_kernel(d, pl.nt, a.main_smem);
+    int best_cpg = 0, best_cc = 0, best_ws = 1;
     double best_cost = 1e300;
     for (int cpg = 1; cpg <= 64; cpg *= 2) {
       if (tn.cpg && cpg != tn.cpg) continue;
@@ -141,25 +144,40 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
       const int real_cpg = (gs + cc - 1) / cc;
       const int nch = G * real_cpg;
       if (nch > slots) break;
-      const int cpc = std::max(1, std::min(slots / nch, Ro));
+      int cpc = std::max(1, std::min(slots / nch, Ro));
+      if (nch >= 2 && nch <= 8 && dev.device >= 0 && fn_probe && tn.cluster != 0) {
+        const int n = max_active_clusters(reinterpret_cast<const void*>(fn_probe), nch, a.warps * 32, 200 * 1024,
+                                          dev.smem_optin);
+        if (n > 0) cpc = std::min(cpc, n);
+      }
       const int rows_cta = (Ro + cpc - 1) / cpc;
-      double cost = double(rows_cta) * cc + 600.0 + 0.35 * cc;
-      cost += (nch <= 8 ? 24.0 : 96.0) * rows_cta;
-      cost *= 1.0 + 0.01 * ilog2(real_cpg);  // ties go to fewer, wider chunks
-      if (rows_cta < a.warps / 2) cost *= 1.0 + 0.6 * (a.warps / 2 - rows_cta) / double(a.warps);
-      if (cost < best_cost) best_cost = cost, best_cpg = real_cpg, best_cc = cc;
+      for (int ws = 1; ws <= 4; ws *= 2) {
+        if (tn.wsplit && ws != tn.wsplit) continue;
+        const int sub = int(align_up(size_t((cc + ws - 1) / ws), 128));
+        if (ws > 1 && (sub < 256 || (ws - 1) * sub >= cc)) continue;
+        const int nslots = a.warps / ws;
+        const int rounds = (rows_cta + nslots - 1) / nslots;
+        const double util = double(rows_cta) * ws / (double(rounds) * a.warps);
+        double cost = double(rows_cta) * cc * (1.0 + 0.5 * (1.0 - util)) + 600.0 + 0.35 * cc;
+        cost += (nch <= 8 ? 24.0 : 96.0) * rows_cta + (ws > 1 ? 16.0 * rows_cta : 0.0);
+        cost *= 1.0 + 0.01 * ilog2(real_cpg);  // ties go to fewer, wider chunks
+        if (cost < best_cost) best_cost = cost, best_cpg = real_cpg, best_cc = cc, best_ws = ws;
+      }
     }
     if (!best_cpg) {  // very wide single group: the widest legal chunk
       best_cc = kMaxChunkCols;
       best_cpg = (gs + kMaxChunkCols - 1) / kMaxChunkCols;
+      best_ws = 1;
     }
     pl.chunk_cols = best_cc, pl.cpg = best_cpg, pl.nch = G * best_cpg;
+    pl.wsplit = best_ws;
+    pl.sub_cols = best_ws > 1 ? int(align_up(size_t((best_cc + best_ws - 1) / best_ws), 128)) : best_cc;
     if (pl.nch > slots) continue;
     pl.cpc = std::max(1, std::min(slots / pl.nch, Ro));
     const int rows_cta = (Ro + pl.cpc - 1) / pl.cpc;
-    // cluster reduce: the leader holds every row's chunk partials; cpc may still be clamped to the
-    // co-schedulable cluster count below, hence 25% slack
-    const size_t part_bytes = size_t(rows_cta + rows_cta / 4 + 1) * pl.nch * pl.nt * v * 4;
+    const int rows_alloc = rows_cta + rows_cta / 4 + 1;  // cpc may still be clamped below: 25% slack
+    // cluster reduce: the leader holds every row's chunk partials
+    const size_t part_bytes = size_t(rows_alloc) * pl.nch * pl.nt * v * 4;
     pl.cluster = (pl.nch >= 2 && pl.nch <= 8 && part_bytes <= kMaxClusterPartBytes && tn.cluster != 0) ? 1 : 0;
     pl.main_in_smem = a.main_smem ? 1 : 0;
     pl.main_rep = a.main_smem ? main_rep_smem : 1;
@@ -182,6 +200,10 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
       off += align_up(size_t(pl.nt) * pl.sx_stride * 4, 128);
       pl.off_part = uint32_t(off);
       if (pl.cluster) off += align_up(part_bytes, 128);
+      pl.off_wsum = uint32_t(off);
+      if (pl.wsplit > 1) off += align_up(size_t(rows_alloc) * pl.wsplit * pl.nt * v * 4, 128);
+      pl.off_wcnt = uint32_t(off);
+      if (pl.wsplit > 1) off += align_up(size_t(rows_alloc) * 4, 128);
       pl.off_res = uint32_t(off);
       off += align_up(res_bytes * res_rep, 128);
       pl.off_main = uint32_t(off);
@@ -203,7 +225,9 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
         for (int rep : {res_rep_max, 1})
           for (int st : {3, 2}) shapes.push_back({st, nb, rep});
     } else {
-      for (int st : {4, 3, 2})
+      // L2-gather layers: a small footprint leaves more of the 256 KB L1/shared array to cache
+      // codebook lines (measured: 2 stages beat 4); smem-resident codebooks take the deeper ring
+      for (int st : (a.main_smem ? std::vector<int>{4, 3, 2} : std::vector<int>{2}))
         for (int rep : {res_rep_max, 1}) shapes.push_back({st, 0, rep});
     }
     bool placed = false;
@@ -212,7 +236,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
       if (tn.stages && sh.stages != tn.stages) continue;
       const size_t need = carve(a.warps, sh.stages, sh.nb, sh.rep);
       if (need <= size_t(smem_limit)) {
-        pl.threads = a.warps * 32, pl.stages = sh.stages, pl.gstages = sh.nb, pl.smem_bytes = uint32_t(need);
+        pl.threads = a.warps * 32, pl.stages = sh.stages, pl.smem_bytes = uint32_t(need);
         placed = true;
         break;
       }
@@ -221,13 +245,13 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
 
     // ---- clusters must all be co-resident: a second wave would double the kernel ----------------
     if (pl.cluster && dev.device >= 0) {
-      GemvKernelFn fn = pick_kernel(d, pl.nt, a.main_smem);
+      GemvKernelFn fn = fn_probe;
       const int n = fn ? max_active_clusters(reinterpret_cast<const void*>(fn), pl.nch, pl.threads,
                                              int(pl.smem_bytes), dev.smem_optin)
                        : -1;
       if (n > 0 && n < pl.cpc) pl.cpc = n;
       const int rows2 = (Ro + pl.cpc - 1) / pl.cpc;
-      if (size_t(rows2) * pl.nch * pl.nt * v * 4 > align_up(part_bytes, 128)) pl.cluster = 0;
+      if (rows2 > rows_alloc) pl.cluster = 0;
     }
     pl.grid = pl.nch * pl.cpc;
     pl.ws_counters_bytes = kCounterRegionBytes;
@@ -277,6 +301,8 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
   p.perm = d.perm;
   p.scale = d.weight_scale;
   p.wbias = d.weight_bias;
+  p.scale_q = d.weight_scale_q;
+  p.wbias_q = d.weight_bias_q;
   p.bias = d.bias;
   p.x_stride = x_stride, p.y_stride = y_stride;
   p.counters = reinterpret_cast<uint32_t*>(workspace);

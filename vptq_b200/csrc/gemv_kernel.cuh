@@ -43,6 +43,8 @@ struct GemvParams {
   const uint16_t* perm;
   const void* scale;
   const void* wbias;
+  const void* scale_q;  // optional load-time copies in quantised column order: scale[perm[c]], wbias[perm[c]]
+  const void* wbias_q;
   const void* bias;
   // activations
   const void* x;
@@ -134,6 +136,8 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   float* s_wb = reinterpret_cast<float*>(smem + pl.off_wb);
   float* sx = reinterpret_cast<float*>(smem + pl.off_sx);
   float* s_part = reinterpret_cast<float*>(smem + pl.off_part);
+  float* s_wsum = reinterpret_cast<float*>(smem + pl.off_wsum);       // [rows][wsplit][NT][V] (wsplit > 1)
+  uint32_t* s_wcnt = reinterpret_cast<uint32_t*>(smem + pl.off_wcnt);  // [rows] arrival counters
   uint8_t* s_res = smem + pl.off_res;
   uint8_t* s_main = smem + pl.off_main;
   uint8_t* s_raw = smem + pl.off_raw;  // TMA landing zone of tables that are then replicated
@@ -156,6 +160,8 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     // leader: every chunk (this one included) delivers NT*V floats per row with st.async
     if (pl.cluster && chunk == 0) mbar_arrive_expect_tx(part_bar, uint32_t(pl.nch * nrows_cta * NT * V) * 4u);
   }
+  if (pl.wsplit > 1)
+    for (int i = tid; i < nrows_cta; i += blockDim.x) s_wcnt[i] = 0u;
   __syncthreads();
   if (pl.cluster) cluster_arrive();  // "this CTA runs and its barriers exist"; waited before the first st.async
   pdl_launch_dependents();           // the next kernel may start its own weight-only prologue now
@@ -164,17 +170,22 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   const uint64_t pol_keep = policy_evict_last();
 
   // -------- work list of this warp -------------------------------------------------------
-  const int nunits = warp < nrows_cta ? (nrows_cta - warp + nwarps - 1) / nwarps : 0;
-  const int nseg = (ncols + pl.seg_fields - 1) / pl.seg_fields;
+  // `wsplit` warps share one row of the chunk: warp w works on column sub-range `wsub` of the rows
+  // of row slot `wslot`; their partial sums meet in shared memory (finish_row).
+  const int wsplit = pl.wsplit, wsub = warp % wsplit, wslot = warp / wsplit, nslots = nwarps / wsplit;
+  const int sf0 = min(ncols, wsub * pl.sub_cols), sf1 = min(ncols, sf0 + pl.sub_cols);  // relative to the chunk
+  const int wcols = sf1 - sf0;
+  const int nunits = wslot < nrows_cta ? (nrows_cta - wslot + nslots - 1) / nslots : 0;
+  const int nseg = (wcols + pl.seg_fields - 1) / pl.seg_fields;
   const int total = nunits * nseg;
   const uint32_t* idx_g = p.indices + int64_t(g) * p.idx_stride_g;
 
   // warp-collective: start the copy of segment q of this warp's work list into its ring stage
   auto issue = [&](int q) {
     const int u = q / nseg, s = q - u * nseg;
-    const int r = cta_in_chunk + pl.cpc * (warp + nwarps * u);
-    const int fs = f0 + s * pl.seg_fields;
-    const int nf = min(pl.seg_fields, f1 - fs);
+    const int r = cta_in_chunk + pl.cpc * (wslot + nslots * u);
+    const int fs = f0 + sf0 + s * pl.seg_fields;
+    const int nf = min(pl.seg_fields, f0 + sf1 - fs);
     const uint32_t* src = idx_g + int64_t(r) * p.idx_stride_r + ((int64_t(fs) * b) >> 5);
     const int nw = (nf * b + 31) >> 5;
     const int st = q % pl.stages;
@@ -241,19 +252,33 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   // four columns per thread and step, loads grouped by dependence level (perm -> scale, wbias)
   const T* scale = reinterpret_cast<const T*>(p.scale);
   const T* wbias = reinterpret_cast<const T*>(p.wbias);
+  const T* scale_q = reinterpret_cast<const T*>(p.scale_q);
+  const T* wbias_q = reinterpret_cast<const T*>(p.wbias_q);
+  // the 1 MiB codebook of an L2-gather layer is cold (2.6 GB of other layers went through the L2
+  // since its last use): pull this CTA's slice of it towards L2 while the prologue runs
+  if constexpr (!MAIN_SMEM) {
+    if (tid == 32) {
+      const uint32_t total_b = uint32_t(p.K) * EB;
+      const uint32_t slice = ((total_b + gridDim.x - 1) / gridDim.x + 15u) & ~15u;
+      const uint32_t off = blockIdx.x * slice;
+      if (off < total_b) l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(cent_g) + off, min(slice, total_b - off));
+    }
+  }
   for (int i0 = tid; i0 < n_all; i0 += 4 * blockDim.x) {
-    int pc[4];
+    int pc[4], cc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = i0 + k * blockDim.x;
       const int c = i < ncols ? p.S + g * p.gs + f0 + i : i - ncols;
+      cc[k] = i < n_all ? c : 0;
       pc[k] = i < n_all ? (p.perm ? int(p.perm[c]) : c) : 0;
     }
     float sc[4], wb[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      sc[k] = scale ? DT<T>::to_float(scale[pc[k]]) : 1.f;
-      wb[k] = wbias ? DT<T>::to_float(wbias[pc[k]]) : 0.f;
+      // quantised-order copies (built once at load time) cut the perm -> scale dependent-load chain
+      sc[k] = scale_q ? DT<T>::to_float(scale_q[cc[k]]) : (scale ? DT<T>::to_float(scale[pc[k]]) : 1.f);
+      wb[k] = wbias_q ? DT<T>::to_float(wbias_q[cc[k]]) : (wbias ? DT<T>::to_float(wbias[pc[k]]) : 0.f);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -353,7 +378,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   // one row of this warp is complete: outlier columns, warp reduction, hand-off
   auto finish_row = [&](int krow) {
     const int r = cta_in_chunk + pl.cpc * krow;
-    if (owns_outliers) {
+    if (owns_outliers && wsub == 0) {
       const T* ocb = reinterpret_cast<const T*>(p.outlier_cb);
       const float* sxo = sx + ncols;
       for (int c = lane; c < p.S; c += 32) {
@@ -373,13 +398,39 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
         }
       }
     }
-    float mine[NT];  // lane e < V: sum of output e of this row over the chunk's columns
+    float mine[NT];  // lane e < V: sum of output e of this row over this warp's columns
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
-      mine[t] = warp_reduce_to_lane<V>(acc[t], lane) + s_cbias[t];
+      mine[t] = warp_reduce_to_lane<V>(acc[t], lane);
 #pragma unroll
       for (int e = 0; e < V; ++e) acc[t][e] = 0.f;
     }
+    if (wsplit > 1) {
+      // the warps sharing this row meet here: each parks its V*NT sums, the last one to arrive adds
+      // them up in sub-range order (deterministic) and carries on alone
+      float* slot = s_wsum + (krow * wsplit) * (NT * V);
+      if (lane < V) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) slot[(wsub * NT + t) * V + lane] = mine[t];
+      }
+      __threadfence_block();
+      __syncwarp();
+      uint32_t prev = 0;
+      if (lane == 0) prev = atomicAdd(&s_wcnt[krow], 1u);
+      prev = __shfl_sync(0xffffffffu, prev, 0);
+      if (prev != uint32_t(wsplit - 1)) return;
+      __threadfence_block();
+      if (lane < V) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          float v = 0.f;
+          for (int w = 0; w < wsplit; ++w) v += slot[(w * NT + t) * V + lane];
+          mine[t] = v;
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; ++t) mine[t] += s_cbias[t];
     const int o = r * V + lane;
     const bool writer = lane < V && o < p.O;
     if (pl.nch == 1) {
@@ -431,7 +482,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     // independent gathers in flight at all times, across segment and row boundaries.  Segment and
     // row boundaries always fall between U-blocks (rows are padded to whole blocks).
     const int gps = pl.seg_fields >> 5;                 // groups per ring segment (multiple of U)
-    const int ngu = ((ncols + 32 * U - 1) / (32 * U)) * U;  // groups per unit, padded to whole U-blocks
+    const int ngu = ((wcols + 32 * U - 1) / (32 * U)) * U;  // groups per unit, padded to whole U-blocks
     const int NG = nunits * ngu;                        // (padding groups decode to field 0, x' = 0)
     uint32_t fld[U];
     uint32_t cw[U][V / 2];
@@ -444,7 +495,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
       if (gs_ == 0) {  // first group of a ring segment: wait for its TMA, once
         mbar_wait(&full[l_st], l_par);
         l_sw = reinterpret_cast<const uint32_t*>(ring + l_st * pl.stage_bytes);
-        l_nf = min(pl.seg_fields, ncols - (l_gl / gps) * pl.seg_fields);
+        l_nf = min(pl.seg_fields, wcols - (l_gl / gps) * pl.seg_fields);
       }
       const uint32_t f = field_at(l_sw, gs_ * 32 + lane, l_nf);
       f_out = f;
@@ -465,12 +516,12 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     for (int n0 = 0; n0 < NG; n0 += U) {
 #pragma unroll
       for (int k = 0; k < U; ++k) {
-        const int j = (c_gl + k) * 32 + lane;  // column of this lane's field, relative to the chunk
+        const int j = (c_gl + k) * 32 + lane;  // this lane's field, relative to the warp's sub-range
         uint32_t rw[V / 2];
         if constexpr (RES) lds_entry<V>(rw, s_res_lane + (fld[k] >> p.ib) * res_stride);
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const float xv = j < ncols ? sx[t * pl.sx_stride + j] : 0.f;
+          const float xv = j < wcols ? sx[t * pl.sx_stride + sf0 + j] : 0.f;
           fma_entry<T, V, RES>(acc[t], xv, cw[k], rw);
         }
         if (n0 + k + U < NG) load(fld[k], cw[k]);  // refill the slot: group n0+k+U
@@ -482,12 +533,15 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
         if (c_q + pl.stages < total) issue(c_q + pl.stages);
         ++c_q;
         if (unit_done) {
-          finish_row(warp + nwarps * c_u);
+          finish_row(wslot + nslots * c_u);
           c_gl = 0, ++c_u;
         }
       }
     }
   }
+
+  if (wsplit > 1 && wcols == 0)  // (ragged last chunk) nothing to add, but the row's other warps count on us
+    for (int u = 0; u < nunits; ++u) finish_row(wslot + nslots * u);
 
   // -------- cluster epilogue: the leader sums the chunks in order and writes y ---------------
   if (pl.cluster && chunk == 0) {

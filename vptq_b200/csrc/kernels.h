@@ -58,8 +58,10 @@ struct GemvPlan {
   int sx_stride;       // floats per token row of x' in smem
   int cluster;         // 1: the nch CTAs of a row set form a thread-block cluster (DSMEM split-K)
   int ctas_per_sm;     // co-resident CTAs per SM the plan was sized for
-  int gstages;         // reserved (0)
-  uint32_t off_bars, off_cbias, off_pcol, off_wb, off_sx, off_part, off_res, off_main, off_raw, off_ring;
+  int wsplit;          // warps sharing one row of the chunk (1, 2 or 4); their sums meet in smem
+  int sub_cols;        // columns per warp sub-range (multiple of 128)
+  uint32_t off_bars, off_cbias, off_pcol, off_wb, off_sx, off_part, off_wsum, off_wcnt, off_res, off_main, off_raw,
+      off_ring;
   uint32_t stage_bytes;
   uint32_t smem_bytes;
   // workspace carve-up

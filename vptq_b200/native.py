@@ -20,7 +20,7 @@ LIB_PATH = os.path.join(_HERE, "libvptq_b200.so")
 VPTQ_FP16, VPTQ_BF16 = 0, 1
 OP_GEMV, OP_DEQUANT, OP_GEMM, OP_GEMV_V2 = 0, 1, 2, 3
 FLAG_PDL = 1
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EXPORTS = (
     "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
@@ -43,7 +43,7 @@ class LinearDesc(ctypes.Structure):
         ("res_centroids", ctypes.c_void_p), ("res_centroid_stride", ctypes.c_int64),
         ("outlier_indices", ctypes.c_void_p), ("outlier_centroids", ctypes.c_void_p),
         ("perm", ctypes.c_void_p), ("weight_scale", ctypes.c_void_p), ("weight_bias", ctypes.c_void_p),
-        ("bias", ctypes.c_void_p),
+        ("bias", ctypes.c_void_p), ("weight_scale_q", ctypes.c_void_p), ("weight_bias_q", ctypes.c_void_p),
     ]
 
 
@@ -122,8 +122,14 @@ def make_desc(*, dtype: torch.dtype, in_features: int, out_features: int, vector
               centroids: torch.Tensor, res_centroids: Optional[torch.Tensor],
               outlier_indices: Optional[torch.Tensor], outlier_centroids: Optional[torch.Tensor],
               perm: Optional[torch.Tensor], weight_scale: Optional[torch.Tensor],
-              weight_bias: Optional[torch.Tensor], bias: Optional[torch.Tensor]) -> LinearDesc:
-    """Describe one layer's tensors for the C ABI.  Tensors are borrowed: keep them alive."""
+              weight_bias: Optional[torch.Tensor], bias: Optional[torch.Tensor],
+              derive: bool = True) -> LinearDesc:
+    """Describe one layer's tensors for the C ABI.  Tensors are borrowed: keep them alive.
+
+    With `derive` (default) the load-time derivatives the ABI accepts are built here, once:
+    weight_scale / weight_bias in quantised column order (`t[perm]`).  They hang off the returned
+    descriptor (`desc._keep`) so they live as long as it does.
+    """
     if indices.dtype != torch.int32:
         raise RuntimeError("`indices` must be packed int32 words (is_indice_packed=True); "
                            "see vptq_b200.pack.pack_index")
@@ -155,6 +161,12 @@ def make_desc(*, dtype: torch.dtype, in_features: int, out_features: int, vector
     d.perm = _ptr(perm)
     d.weight_scale, d.weight_bias = _ptr(weight_scale), _ptr(weight_bias)
     d.bias = _ptr(bias)
+    d._keep = ()
+    if derive and perm is not None and weight_scale is not None and weight_bias is not None:
+        pidx = perm.view(torch.uint16).to(torch.int64) if perm.dtype in (torch.int16, torch.uint16) else perm.long()
+        ws_q, wb_q = weight_scale[pidx].contiguous(), weight_bias[pidx].contiguous()
+        d.weight_scale_q, d.weight_bias_q = ws_q.data_ptr(), wb_q.data_ptr()
+        d._keep = (ws_q, wb_q)
     return d
 
 
