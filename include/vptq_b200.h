@@ -125,6 +125,11 @@ typedef enum vptq_op {
   VPTQ_OP_GEMV_V2 = 3  /* vptq_b200_quant_gemv_v2 */
 } vptq_op;
 
+/* Developer aid (not needed by any caller): when given a device buffer of 32 uint64, every GEMV
+   launched afterwards records %globaltimer stamps of its phases (first and last CTA) there;
+   NULL switches it off again.  See tools/profile_gemv.py --phases. */
+VPTQ_B200_API void vptq_b200_debug_phase_stamps(void* device_buffer);
+
 /* Library / device probing.  No GPU work. */
 VPTQ_B200_API int vptq_b200_abi_version(void);
 VPTQ_B200_API const char* vptq_b200_last_error(void);

@@ -20,7 +20,11 @@ cfgs = {"b24_k65536_r256": bench.QUANT,
         "b21_k8192_r256": dict(vector_len=8, num_centroids=8192, num_res_centroids=256),
         "b12_k4096": dict(vector_len=8, num_centroids=4096, num_res_centroids=-1),
         "b8_k256": dict(vector_len=8, num_centroids=256, num_res_centroids=-1)}
-only = sys.argv[1:] or list(cfgs)
+PHASES = "--phases" in sys.argv
+only = [a for a in sys.argv[1:] if not a.startswith("--")] or list(cfgs)
+prof = torch.zeros(32, dtype=torch.int64, device=dev)
+NAMES = ["start", "bar_init", "issued+staged", "phaseA", "cb_wait+replicate", "pdl_wait", "phaseB+sync", "cluster_wait",
+         "main(warp0)", "leader_wait", "end"]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 out = {}
 for cname in only:
@@ -58,6 +62,18 @@ for cname in only:
         for _ in range(20):
             native.quant_gemv(desc, x, y)
         e1.record(); torch.cuda.synchronize()
+        if PHASES:
+            flush.fill_(1)
+            native.lib().vptq_b200_debug_phase_stamps(prof.data_ptr())
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); native.quant_gemv(desc, x, y); e1.record(); torch.cuda.synchronize()
+            native.lib().vptq_b200_debug_phase_stamps(None)
+            st = prof.cpu().tolist()
+            for base, who in ((0, "cta0"), (16, "ctaN")):
+                t0 = st[base]
+                print(f"   {who}: " + "  ".join(f"{NAMES[k]}={(st[base + k] - t0) / 1e3:.2f}" for k in range(1, 11) if st[base + k]),
+                      f"| event {e0.elapsed_time(e1) * 1e3:.1f} us", flush=True)
+            prof.zero_()
         abytes = ro * wd * 4 + i * 2 + o * 2
         us = sorted(ts)[len(ts) // 2]
         out[f"{cname}/{name}"] = dict(cold_us=round(us, 2), warm_us=round(e0.elapsed_time(e1) * 1e3 / 20, 2),

@@ -152,6 +152,8 @@ extern "C" {
 
 int vptq_b200_abi_version(void) { return VPTQ_B200_ABI_VERSION; }
 
+void vptq_b200_debug_phase_stamps(void* device_buffer) { gemv_set_profile_buffer(device_buffer); }
+
 const char* vptq_b200_last_error(void) { return g_error; }
 
 size_t vptq_b200_workspace_bytes(const vptq_linear_desc* desc, int32_t tokens, int32_t op) {

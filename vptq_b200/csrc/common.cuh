@@ -201,6 +201,9 @@ __device__ __forceinline__ void st_async_f32(uint32_t remote_addr, float v, uint
                "r"(__float_as_uint(v)), "r"(remote_bar)
                : "memory");
 }
+__device__ __forceinline__ void cluster_arrive_relaxed() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 

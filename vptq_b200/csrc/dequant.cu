@@ -26,6 +26,9 @@ struct DequantParams {
   const void* scale;
   const void* wbias;
   void* out;
+  int64_t ld;       // output row pitch in elements
+  int quant_order;  // 1: columns stay in quantised order, no scale / bias (tensor-core operand of the prefill GEMM);
+                    //    columns [I, ld) are zero-filled
   int I, O, Ro, G, gs, S, vol;
   int ib, rb;
 };
@@ -39,7 +42,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256) dequant_kernel(const __grid_constant__ DequantParams p) {
   const int r = blockIdx.y;
   const int fbase = (blockIdx.x * blockDim.x + threadIdx.x) * 2;
-  if (fbase >= p.I) return;
+  const int ncols = p.quant_order ? int(p.ld) : p.I;
+  if (fbase >= ncols) return;
   const T* scale = reinterpret_cast<const T*>(p.scale);
   const T* wbias = reinterpret_cast<const T*>(p.wbias);
   const int b = p.ib + p.rb;
@@ -55,9 +59,9 @@ __global__ void __launch_bounds__(256) dequant_kernel(const __grid_constant__ De
       for (int e = 0; e < V; ++e) val[h][e] = 0.f;
       continue;
     }
-    const int c = p.inv_perm ? int(p.inv_perm[f]) : f;
-    const float sc = scale ? DT<T>::to_float(scale[f]) : 1.f;
-    const float wb = wbias ? DT<T>::to_float(wbias[f]) : 0.f;
+    const int c = (p.inv_perm && !p.quant_order) ? int(p.inv_perm[f]) : f;
+    const float sc = (scale && !p.quant_order) ? DT<T>::to_float(scale[f]) : 1.f;
+    const float wb = (wbias && !p.quant_order) ? DT<T>::to_float(wbias[f]) : 0.f;
     if (c < p.S) {  // outlier column: its own codebook with vector length `vol`
       const T* ocb = reinterpret_cast<const T*>(p.outlier_cb);
 #pragma unroll
@@ -104,24 +108,25 @@ __global__ void __launch_bounds__(256) dequant_kernel(const __grid_constant__ De
   }
 
   T* out = reinterpret_cast<T*>(p.out);
-  const bool pair = (fbase + 1 < p.I) && ((p.I & 1) == 0);
+  const bool pair = (fbase + 1 < ncols) && ((p.ld & 1) == 0);
 #pragma unroll
   for (int e = 0; e < V; ++e) {
     const int o = r * V + e;
     if (o >= p.O) break;  // padding rows are dropped (vptq/ops/quant_gemm.py:123-124)
-    T* dst = out + int64_t(o) * p.I + fbase;
+    T* dst = out + int64_t(o) * p.ld + fbase;
     if (pair) {
       *reinterpret_cast<uint32_t*>(dst) = DT<T>::pack2(val[0][e], val[1][e]);
     } else {
       dst[0] = DT<T>::from_float(val[0][e]);
-      if (fbase + 1 < p.I) dst[1] = DT<T>::from_float(val[1][e]);
+      if (fbase + 1 < ncols) dst[1] = DT<T>::from_float(val[1][e]);
     }
   }
 }
 
 template <typename T>
 int launch_v(const DequantParams& p, int v, cudaStream_t stream) {
-  dim3 block(256), grid(unsigned((p.I + 511) / 512), unsigned(p.Ro));
+  const int ncols = p.quant_order ? int(p.ld) : p.I;
+  dim3 block(256), grid(unsigned((ncols + 511) / 512), unsigned(p.Ro));
   switch (v) {
 #define VPTQ_CASE(VV) \
   case VV: dequant_kernel<T, VV><<<grid, block, 0, stream>>>(p); break;
@@ -161,6 +166,8 @@ int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size
   p.outlier_cb = p.S ? d.outlier_centroids : nullptr;
   p.scale = d.weight_scale, p.wbias = d.weight_bias;
   p.out = w_out;
+  p.ld = d.in_features;
+  p.quant_order = 0;
   p.inv_perm = nullptr;
   if (d.perm) {
     const size_t need = dequant_workspace_bytes(d);
@@ -176,6 +183,27 @@ int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size
                                       : launch_v<__nv_bfloat16>(p, d.vector_len, stream);
   if (rc) return rc;
   return 0;
+}
+
+// Wq[o][c] = C[idx] + R[ridx] (outlier columns from their own codebook) in QUANTISED column order,
+// row pitch `ld`, columns [I, ld) zero: the B operand of the prefill GEMM (gemm_tcgen05.cu).
+int dequant_quant_order_launch(const vptq_linear_desc& d, void* wq_out, int64_t ld, cudaStream_t stream) {
+  DequantParams p{};
+  p.indices = reinterpret_cast<const uint32_t*>(d.indices);
+  p.idx_stride_g = d.index_stride_codebook, p.idx_stride_r = d.index_stride_row;
+  p.centroids = d.centroids, p.cb_stride = d.centroid_stride;
+  p.res_centroids = d.res_centroids, p.rcb_stride = d.res_centroid_stride;
+  p.I = d.in_features, p.O = d.out_features, p.G = d.num_codebooks, p.gs = d.group_size;
+  p.Ro = (d.out_features + d.vector_len - 1) / d.vector_len;
+  p.ib = ilog2(d.num_centroids);
+  p.rb = d.num_res_centroids > 0 ? ilog2(d.num_res_centroids) : 0;
+  p.S = (d.outlier_size > 0 && d.outlier_indices) ? d.outlier_size : 0;
+  p.vol = p.S ? d.outlier_vector_len : 1;
+  p.outlier_idx = p.S ? d.outlier_indices : nullptr;
+  p.outlier_cb = p.S ? d.outlier_centroids : nullptr;
+  p.out = wq_out, p.ld = ld, p.quant_order = 1;
+  return d.dtype == VPTQ_FP16 ? launch_v<__half>(p, d.vector_len, stream)
+                              : launch_v<__nv_bfloat16>(p, d.vector_len, stream);
 }
 
 }  // namespace vptq_b200

@@ -1,0 +1,378 @@
+// Prefill path: y[T][O] = x[T][I] * W[O][I]^T + bias for many tokens, on the 5th-generation tensor
+// cores (tcgen05.mma, accumulator in TMEM, operands staged in shared memory by TMA).
+//
+// Replaces the reference's tokens >= 3 branch (vptq/ops/quant_gemm.py:231-275: the `dequant` CUDA
+// op followed by torch F.linear / cuBLAS).  The algebra is rearranged so that the tensor-core
+// operand is the RAW quantised weight (no per-column scale / bias / permutation inside the GEMM):
+//
+//   y[t][o] = sum_c x'[t][c] * Wq[o][c]  +  rowbias[t]  +  bias[o]
+//   x'[t][c]   = x[t][perm[c]] * scale[perm[c]]                 (prep kernel, one pass over x)
+//   rowbias[t] = sum_f x[t][f] * wbias[f]                        (same kernel, fp32)
+//   Wq[o][c]   = C[idx[o/v][c]][o%v] + R[ridx[o/v][c]][o%v]      (outlier columns from their codebook)
+//
+// Three kernels on the caller's stream:
+//   1. prefill_prep_x     x -> x' (16 bit, quantised column order) and rowbias (fp32)
+//   2. dequant (dequant.cu, quantised-order mode)  packed indices -> Wq tile source [O][Ipad]
+//   3. gemm_tn_tcgen05    warp-specialised: TMA producer / single-thread MMA issuer / 4 epilogue warps,
+//                         128x128x64 tiles, 6-stage smem ring, fp32 accumulator in 128 TMEM columns,
+//                         epilogue adds rowbias[t] + bias[o] and writes 16-bit y.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vptq_b200 {
+
+// implemented in dequant.cu
+int dequant_quant_order_launch(const vptq_linear_desc& d, void* wq_out, int64_t ld, cudaStream_t stream);
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;  // CTA tile: tokens x outputs x reduction
+constexpr int UMMA_K = 16;                  // K per tcgen05.mma for 16-bit inputs
+constexpr int STAGES = 6;
+constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
+constexpr int TMEM_COLS = 128;              // fp32 accumulator: 128 lanes x 128 columns
+constexpr int GEMM_THREADS = 192;           // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
+constexpr int GEMM_SMEM = STAGES * (TILE_A_BYTES + TILE_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---------------------------------------------------------------------------------------------
+// x' = x[perm] * scale[perm]  and  rowbias = x . wbias
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) prefill_prep_x(const T* __restrict__ x, int64_t x_stride,
+                                                      const uint16_t* __restrict__ perm,
+                                                      const T* __restrict__ scale, const T* __restrict__ wbias,
+                                                      T* __restrict__ xq, int64_t xq_stride,
+                                                      float* __restrict__ rowbias, int I) {
+  const int t = blockIdx.x;
+  const T* xr = x + int64_t(t) * x_stride;
+  T* out = xq + int64_t(t) * xq_stride;
+  float bs = 0.f;
+  for (int c = threadIdx.x; c < I; c += blockDim.x) {
+    const int f = perm ? int(perm[c]) : c;
+    const float xv = DT<T>::to_float(xr[f]);
+    out[c] = DT<T>::from_float(scale ? xv * DT<T>::to_float(scale[f]) : xv);
+    if (wbias) bs = fmaf(xv, DT<T>::to_float(wbias[f]), bs);
+  }
+  for (int c = I + threadIdx.x; c < xq_stride; c += blockDim.x) out[c] = DT<T>::from_float(0.f);  // K padding
+  __shared__ float red[8];
+  bs = warp_sum(bs);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bs;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float v = 0.f;
+    for (int w = 0; w < int(blockDim.x >> 5); ++w) v += red[w];
+    rowbias[t] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tcgen05 / TMA PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem desc] * B[smem desc], issued by ONE thread for the whole CTA
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns of TMEM -> 32 registers per thread (lane i <-> TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major tile whose rows are 128 bytes (64 x 16 bit), 128B swizzle
+// (8-row x 128-byte atoms, 1024 bytes apart), sm_100 descriptor version 1
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= uint64_t((saddr & 0x3FFFFu) >> 4);        // bits [0,14)  start address >> 4
+  d |= uint64_t(0) << 16;                        // bits [16,30) leading-dim byte offset (unused: K-major, swizzled)
+  d |= uint64_t(1024 >> 4) << 32;                // bits [32,46) stride-dim byte offset: next 8-row group
+  d |= uint64_t(1) << 46;                        // bits [46,48) descriptor version (Blackwell)
+  d |= uint64_t(2) << 61;                        // bits [61,64) layout: SWIZZLE_128B
+  return d;
+}
+
+// instruction descriptor, kind::f16: fp32 accumulate, A and B both K-major, M x N tile
+__host__ __device__ constexpr uint32_t umma_idesc(int is_bf16, int m, int n) {
+  return (1u << 4)                        // D format: f32
+         | (uint32_t(is_bf16) << 7)       // A format: 0 f16, 1 bf16
+         | (uint32_t(is_bf16) << 10)      // B format
+         | (0u << 15) | (0u << 16)        // A, B major: K
+         | (uint32_t(n >> 3) << 17)       // N / 8
+         | (uint32_t(m >> 4) << 24);      // M / 16
+}
+
+struct GemmParams {
+  const void* bias;       // [O] 16 bit or nullptr
+  const float* rowbias;   // [T]
+  void* y;
+  int64_t y_stride;
+  int T, O, K;            // K = padded reduction length (multiple of 8)
+  int is_bf16;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles must start on 1024-byte boundaries
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sa = smem;
+  uint8_t* sb = smem + STAGES * TILE_A_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (TILE_A_BYTES + TILE_B_BYTES));
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int nkb = (p.K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (one lane) =====
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);  // slot free (passes immediately in round 0)
+        mbar_arrive_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
+        tma_load_2d(sa + s * TILE_A_BYTES, &map_a, kb * BK, m0, &full[s]);
+        tma_load_2d(sb + s * TILE_B_BYTES, &map_b, kb * BK, n0, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one lane issues for the whole CTA) =====
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc(p.is_bf16, BM, BN);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&full[s], (kb / STAGES) & 1);  // TMA bytes have landed
+        tc_fence_after();
+        const uint64_t da = umma_desc_k_sw128(smem_u32(sa + s * TILE_A_BYTES));
+        const uint64_t db = umma_desc_k_sw128(smem_u32(sb + s * TILE_B_BYTES));
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in 16-byte units
+          umma_f16_ss(tmem_base, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);  // frees this smem slot once the MMAs above have read it
+      }
+      umma_commit(tmem_full);  // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> (+rowbias +bias) -> 16-bit y =====
+    const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int m = m0 + quarter * 32 + lane;
+    const float rb = m < p.T ? p.rowbias[m] : 0.f;
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    T* yrow = reinterpret_cast<T*>(p.y) + int64_t(m) * p.y_stride;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), r);
+      tmem_ld_wait();
+      if (m < p.T) {
+        const int nb = n0 + c0;
+        if (nb + 32 <= p.O && (p.y_stride & 7) == 0 && (nb & 7) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n = nb + j + 2 * i;
+              const float b0 = bias ? DT<T>::to_float(bias[n]) : 0.f, b1 = bias ? DT<T>::to_float(bias[n + 1]) : 0.f;
+              w[i] = DT<T>::pack2(__uint_as_float(r[j + 2 * i]) + rb + b0, __uint_as_float(r[j + 2 * i + 1]) + rb + b1);
+            }
+            *reinterpret_cast<uint4*>(yrow + nb + j) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        } else {
+          for (int j = 0; j < 32; ++j) {
+            const int n = nb + j;
+            if (n < p.O) yrow[n] = DT<T>::from_float(__uint_as_float(r[j]) + rb + (bias ? DT<T>::to_float(bias[n]) : 0.f));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// row-major [rows][cols] 16-bit matrix, row pitch `ld` elements; box = 64 columns x 128 rows, 128B swizzle
+int make_map(CUtensorMap* m, int is_bf16, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) {
+    set_error("quant_gemm: cuTensorMapEncodeTiled not available from the driver");
+    return VPTQ_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(ld) * 2};
+  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("quant_gemm: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", int(r), (long long)rows,
+              (long long)cols, (long long)ld);
+    return VPTQ_ERR_CUDA;
+  }
+  return 0;
+}
+
+struct GemmWorkspace {
+  size_t off_rowbias, off_xq, off_wq, total;
+  int64_t kpad;
+};
+GemmWorkspace gemm_layout(const vptq_linear_desc& d, int tokens) {
+  GemmWorkspace w;
+  w.kpad = int64_t(align_up(size_t(d.in_features), 64));  // whole BK blocks: no partially filled swizzle rows
+  size_t off = kCounterRegionBytes;                      // the zero-at-rest region stays untouched
+  w.off_rowbias = off;
+  off += align_up(size_t(tokens) * 4, 1024);
+  w.off_xq = off;
+  off += align_up(size_t(tokens) * w.kpad * 2, 1024);
+  w.off_wq = off;
+  off += align_up(size_t(d.out_features) * w.kpad * 2, 1024);
+  w.total = off;
+  return w;
+}
+
+std::once_flag g_attr_once[2];
+
+}  // namespace
+
+size_t gemm_workspace_bytes(const vptq_linear_desc& d, int tokens) { return gemm_layout(d, tokens).total; }
+
+int gemm_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void* y, int64_t y_stride, int tokens,
+                void* workspace, size_t workspace_bytes, uint32_t /*flags*/, cudaStream_t stream) {
+  const GemmWorkspace w = gemm_layout(d, tokens);
+  if (!workspace || workspace_bytes < w.total) {
+    set_error("quant_gemm: workspace %zu bytes < required %zu", workspace_bytes, w.total);
+    return VPTQ_ERR_WORKSPACE;
+  }
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* rowbias = reinterpret_cast<float*>(ws + w.off_rowbias);
+  void* xq = ws + w.off_xq;
+  void* wq = ws + w.off_wq;
+  const int is_bf16 = d.dtype == VPTQ_BF16;
+
+  // 1. x' and rowbias
+  if (is_bf16)
+    prefill_prep_x<__nv_bfloat16><<<tokens, 256, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(x), x_stride, d.perm,
+        reinterpret_cast<const __nv_bfloat16*>(d.weight_scale), reinterpret_cast<const __nv_bfloat16*>(d.weight_bias),
+        reinterpret_cast<__nv_bfloat16*>(xq), w.kpad, rowbias, d.in_features);
+  else
+    prefill_prep_x<__half><<<tokens, 256, 0, stream>>>(
+        reinterpret_cast<const __half*>(x), x_stride, d.perm, reinterpret_cast<const __half*>(d.weight_scale),
+        reinterpret_cast<const __half*>(d.weight_bias), reinterpret_cast<__half*>(xq), w.kpad, rowbias,
+        d.in_features);
+  // 2. Wq in quantised column order (no scale / bias / perm)
+  if (int rc = dequant_quant_order_launch(d, wq, w.kpad, stream)) return rc;
+  // 3. tensor-core GEMM
+  CUtensorMap map_a, map_b;
+  if (int rc = make_map(&map_a, is_bf16, xq, tokens, w.kpad, w.kpad)) return rc;
+  if (int rc = make_map(&map_b, is_bf16, wq, d.out_features, w.kpad, w.kpad)) return rc;
+  GemmParams p{};
+  p.bias = d.bias, p.rowbias = rowbias, p.y = y, p.y_stride = y_stride;
+  p.T = tokens, p.O = d.out_features, p.K = int(w.kpad), p.is_bf16 = is_bf16;
+  dim3 grid(unsigned((d.out_features + BN - 1) / BN), unsigned((tokens + BM - 1) / BM));
+  cudaError_t e;
+  if (is_bf16) {
+    std::call_once(g_attr_once[1], [] {
+      cudaFuncSetAttribute(gemm_tn_tcgen05<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    });
+    gemm_tn_tcgen05<__nv_bfloat16><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(map_a, map_b, p);
+  } else {
+    std::call_once(g_attr_once[0], [] {
+      cudaFuncSetAttribute(gemm_tn_tcgen05<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    });
+    gemm_tn_tcgen05<__half><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(map_a, map_b, p);
+  }
+  e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("quant_gemm launch: %s", cudaGetErrorString(e));
+    return VPTQ_ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // namespace vptq_b200

@@ -90,6 +90,10 @@ int max_active_clusters(const void* fn, int csize, int threads, int smem, int op
 
 }  // namespace
 
+// developer aid: phase-stamp buffer (device pointer) handed to every subsequent GEMV launch
+static unsigned long long* g_prof_buffer = nullptr;
+void gemv_set_profile_buffer(void* dev_ptr) { g_prof_buffer = static_cast<unsigned long long*>(dev_ptr); }
+
 int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev, GemvPlan* out) {
   const int v = d.vector_len, G = d.num_codebooks, gs = d.group_size;
   const int Ro = (d.out_features + v - 1) / v;
@@ -312,6 +316,7 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
                   (d.index_stride_codebook & 3) == 0)
                      ? 1
                      : 0;
+  p.prof = g_prof_buffer;
   p.plan = pl;
 
   const size_t esz = 2;

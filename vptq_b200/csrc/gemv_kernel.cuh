@@ -57,6 +57,7 @@ struct GemvParams {
   int I, O, Ro, G, gs, S, vol, Kol, Rol;
   int K, Kr, ib, rb;
   int idx_tma_ok;  // rows are 16-byte aligned -> bulk copies legal
+  unsigned long long* prof;  // developer aid: per-phase %globaltimer stamps of CTA 0 / last CTA (or nullptr)
   GemvPlan plan;
 };
 
@@ -120,6 +121,15 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   const GemvPlan& pl = p.plan;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  // phase stamps (ns) of thread 0 of the first and of the last CTA: tools/profile_gemv.py --phases
+  auto stamp = [&](int slot) {
+    if (p.prof && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      p.prof[(blockIdx.x == 0 ? 0 : 16) + slot] = t;
+    }
+  };
+  stamp(0);
   const int chunk = blockIdx.x % pl.nch;  // == %cluster_ctarank when launched as a cluster
   const int cta_in_chunk = blockIdx.x / pl.nch;
   const int g = chunk / pl.cpg, cig = chunk % pl.cpg;
@@ -152,18 +162,23 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   const int nrows_cta = cta_in_chunk < p.Ro ? (p.Ro - cta_in_chunk + pl.cpc - 1) / pl.cpc : 0;
 
   // -------- barrier init -----------------------------------------------------------------
-  if (tid == 0) {
-    mbar_init(cb_bar, 1);
-    mbar_init(part_bar, 1);
-    for (int i = 0; i < nwarps * pl.stages; ++i) mbar_init(&bars[2 + i], 1);
-    fence_mbar_init();
-    // leader: every chunk (this one included) delivers NT*V floats per row with st.async
-    if (pl.cluster && chunk == 0) mbar_arrive_expect_tx(part_bar, uint32_t(pl.nch * nrows_cta * NT * V) * 4u);
+  {
+    const int nbar = 2 + nwarps * pl.stages;  // one thread per barrier: a serial loop costs ~0.5 us
+    if (tid < nbar) {
+      mbar_init(&bars[tid], 1);
+      fence_mbar_init();
+      // leader: every chunk (this one included) delivers NT*V floats per row with st.async
+      if (tid == 1 && pl.cluster && chunk == 0)
+        mbar_arrive_expect_tx(part_bar, uint32_t(pl.nch * nrows_cta * NT * V) * 4u);
+    }
   }
   if (pl.wsplit > 1)
     for (int i = tid; i < nrows_cta; i += blockDim.x) s_wcnt[i] = 0u;
   __syncthreads();
-  if (pl.cluster) cluster_arrive();  // "this CTA runs and its barriers exist"; waited before the first st.async
+  stamp(1);
+  // "this CTA runs and its barriers exist" (made cluster-visible by fence.mbarrier_init); relaxed: a
+  // releasing arrive costs a GPU-scope MEMBAR (~1 us).  Waited before the first st.async.
+  if (pl.cluster) cluster_arrive_relaxed();
   pdl_launch_dependents();           // the next kernel may start its own weight-only prologue now
 
   const uint64_t pol_stream = policy_evict_first();
@@ -248,6 +263,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     else mbar_arrive(cb_bar);
   }
 
+  stamp(2);
   // -------- x' prologue, phase A: everything that does not depend on x --------------------
   // four columns per thread and step, loads grouped by dependence level (perm -> scale, wbias)
   const T* scale = reinterpret_cast<const T*>(p.scale);
@@ -287,6 +303,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     }
   }
 
+  stamp(3);
   // replicate TMA-landed tables (smem -> smem) once they have arrived
   if constexpr (RES || MAIN_SMEM) mbar_wait(cb_bar, 0);
   if constexpr (V == 8) {
@@ -302,8 +319,10 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     if (MAIN_SMEM && tma_main && pl.main_rep > 1) replicate(s_main, raw_main, p.K);
   }
 
+  stamp(4);
   // -------- phase B: x arrives from the previous kernel ------------------------------------
   pdl_wait_prior_grid();
+  stamp(5);
   {
     const T* x = reinterpret_cast<const T*>(p.x);
     float bs[NT];
@@ -346,7 +365,9 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     }
   }
   __syncthreads();
+  stamp(6);
   if (pl.cluster) cluster_wait();  // every CTA of the cluster runs: the leader's smem may be written
+  stamp(7);
 
   // -------- main loop ------------------------------------------------------------------------
   const uint32_t fmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
@@ -540,12 +561,14 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     }
   }
 
+  stamp(8);  // warp 0 finished its rows
   if (wsplit > 1 && wcols == 0)  // (ragged last chunk) nothing to add, but the row's other warps count on us
     for (int u = 0; u < nunits; ++u) finish_row(wslot + nslots * u);
 
   // -------- cluster epilogue: the leader sums the chunks in order and writes y ---------------
   if (pl.cluster && chunk == 0) {
     mbar_wait(part_bar, 0);  // all nch * nrows_cta * NT * V partial sums have landed
+    stamp(9);
     const int n = nrows_cta * NT * V;
     for (int i = tid; i < n; i += blockDim.x) {
       const int e = i % V, t = (i / V) % NT, krow = i / (V * NT);

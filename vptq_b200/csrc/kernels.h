@@ -71,6 +71,7 @@ struct GemvPlan {
 
 // Fills `plan` for (desc, tokens-per-pass).  Returns 0 or a vptq_status.
 int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev, GemvPlan* plan);
+void gemv_set_profile_buffer(void* dev_ptr);
 // Launches ceil(tokens / plan.nt) passes.
 int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void* y, int64_t y_stride,
                 int tokens, void* workspace, size_t workspace_bytes, uint32_t flags, cudaStream_t stream);

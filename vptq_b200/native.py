@@ -25,6 +25,7 @@ ABI_VERSION = 2
 EXPORTS = (
     "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
     "vptq_b200_dequant", "vptq_b200_quant_gemm", "vptq_b200_quant_gemv_v2", "vptq_b200_linear_host",
+    "vptq_b200_debug_phase_stamps",
 )
 
 
@@ -76,6 +77,8 @@ def lib() -> ctypes.CDLL:
         L.vptq_b200_quant_gemv_v2.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp,
                                               vp, vp, vp, sz, u32, vp]
         L.vptq_b200_linear_host.argtypes = [dp, vp, vp, i32, vp, vp, vp, sz, u32, vp]
+        L.vptq_b200_debug_phase_stamps.argtypes = [vp]
+        L.vptq_b200_debug_phase_stamps.restype = None
         for f in ("vptq_b200_quant_gemv", "vptq_b200_quant_gemm", "vptq_b200_dequant", "vptq_b200_quant_gemv_v2",
                   "vptq_b200_linear_host"):
             getattr(L, f).restype = ctypes.c_int
