@@ -6,6 +6,8 @@
 // Thread mapping: a thread owns two adjacent ORIGINAL columns f, f+1 of one index row, so a warp
 // stores 128 contiguous bytes per output row (the reference stores one 2-byte element per thread
 // and row).  (C + R) * scale + bias is evaluated in fp32 and rounded once.
+#include <mutex>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -123,6 +125,116 @@ __global__ void __launch_bounds__(256) dequant_kernel(const __grid_constant__ De
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path of the quantised-order dequant (the prefill GEMM's B operand), vector_len 8:
+// a thread owns 8 CONSECUTIVE columns of one index row, gathers their 8 codebook entries
+// (8 independent 16-byte loads in flight), adds the residual entries from a bank-replicated
+// shared-memory table, transposes the 8x8 block in registers (PRMT) and writes one 16-byte
+// vector per output row: every warp store covers 512 contiguous bytes.
+// ---------------------------------------------------------------------------------------------
+constexpr int DQ_ROWS = 8, DQ_COLS = 1024, DQ_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(DQ_THREADS) dequant_q8_kernel(const __grid_constant__ DequantParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int b = p.ib + p.rb;
+  const int chunks_per_group = (p.gs + DQ_COLS - 1) / DQ_COLS;
+  const int g = blockIdx.x / chunks_per_group, ch = blockIdx.x % chunks_per_group;
+  const int j0 = ch * DQ_COLS;                         // first column of the chunk inside its group
+  const int ncols = min(DQ_COLS, p.gs - j0);           // multiple of 8
+  const int r0 = blockIdx.y * DQ_ROWS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t row_words = (uint32_t(DQ_COLS) * b + 31) / 32 + 4;  // per staged row, padded
+  uint32_t* s_idx = reinterpret_cast<uint32_t*>(smem);               // [DQ_ROWS][row_words]
+  uint8_t* s_res = smem + ((DQ_ROWS * row_words * 4 + 127) & ~127u); // replicated residual table
+  __shared__ uint64_t bar;
+
+  const uint32_t* idx_g = p.indices + int64_t(g) * p.idx_stride_g;
+  const int nw = (ncols * b + 31) >> 5;
+  const int64_t w0 = (int64_t(j0) * b) >> 5;  // j0 is a multiple of 1024: word aligned
+  const bool tma_ok = ((reinterpret_cast<uintptr_t>(idx_g) & 15u) == 0) && ((p.idx_stride_r & 3) == 0) && ((nw & 3) == 0);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const uint64_t pol = policy_evict_first();
+  if (tma_ok) {
+    if (tid == 0) {
+      int rows = min(DQ_ROWS, p.Ro - r0);
+      mbar_arrive_expect_tx(&bar, uint32_t(rows) * uint32_t(nw) * 4u);
+      for (int i = 0; i < rows; ++i)
+        tma_bulk_g2s(s_idx + i * row_words, idx_g + int64_t(r0 + i) * p.idx_stride_r + w0, uint32_t(nw) * 4u, &bar, pol);
+    }
+  } else {
+    for (int i = 0; i < DQ_ROWS && r0 + i < p.Ro; ++i)
+      for (int w = tid; w < nw; w += DQ_THREADS) s_idx[i * row_words + w] = ldg_nc_u32(idx_g + int64_t(r0 + i) * p.idx_stride_r + w0 + w);
+  }
+  // residual table: 8 copies of every 16-byte entry, copy k at slot i*8+k (lane L reads copy L&7)
+  const T* rcb = p.rb ? reinterpret_cast<const T*>(p.res_centroids) + int64_t(g) * p.rcb_stride : nullptr;
+  const int Kr = p.rb ? (1 << p.rb) : 0;
+  for (int e = tid; e < Kr; e += DQ_THREADS) {
+    const uint4 v = ldg_nc_v4(reinterpret_cast<const uint8_t*>(rcb) + size_t(e) * 16, policy_evict_last());
+#pragma unroll
+    for (int c = 0; c < 8; ++c) sts_v4(smem_u32(s_res) + (e * 8 + c) * 16, v);
+  }
+  __syncthreads();
+  if (tma_ok) mbar_wait(&bar, 0);
+
+  const int r = r0 + warp;
+  if (r >= p.Ro) return;
+  const uint32_t fmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u), imask = (1u << p.ib) - 1u;
+  const uint32_t* sw = s_idx + warp * row_words;
+  const uint8_t* cb = reinterpret_cast<const uint8_t*>(reinterpret_cast<const T*>(p.centroids) + int64_t(g) * p.cb_stride);
+  const uint32_t res_lane = smem_u32(s_res) + (lane & 7) * 16;
+  const uint64_t keep = policy_evict_last();
+  T* out = reinterpret_cast<T*>(p.out);
+  const int col_base = p.S + g * p.gs + j0;  // quantised column of the chunk's first field
+
+  for (int jc = lane * 8; jc < ncols; jc += 32 * 8) {
+    uint32_t fld[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t bit = uint32_t(jc + k) * uint32_t(b), w = bit >> 5;
+      fld[k] = __funnelshift_r(sw[w], sw[w + 1], bit & 31u) & fmask;
+    }
+    uint4 cw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cw[k] = ldg_nc_v4(cb + size_t(fld[k] & imask) * 16, keep);
+    if (p.rb) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const uint4 rw = lds_v4(res_lane + (fld[k] >> p.ib) * 128);
+        cw[k].x = DT<T>::add2(cw[k].x, rw.x), cw[k].y = DT<T>::add2(cw[k].y, rw.y);
+        cw[k].z = DT<T>::add2(cw[k].z, rw.z), cw[k].w = DT<T>::add2(cw[k].w, rw.w);
+      }
+    }
+    // 8x8 transpose: output row e takes element e of each of the 8 entries
+    const uint32_t* cwp = reinterpret_cast<const uint32_t*>(cw);  // cw[k] word i = cwp[4*k + i]
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int o = r * 8 + e;
+      if (o < p.O) {
+        const uint32_t sel = (e & 1) ? 0x7632u : 0x5410u;
+        uint4 v;
+        v.x = __byte_perm(cwp[4 * 0 + (e >> 1)], cwp[4 * 1 + (e >> 1)], sel);
+        v.y = __byte_perm(cwp[4 * 2 + (e >> 1)], cwp[4 * 3 + (e >> 1)], sel);
+        v.z = __byte_perm(cwp[4 * 4 + (e >> 1)], cwp[4 * 5 + (e >> 1)], sel);
+        v.w = __byte_perm(cwp[4 * 6 + (e >> 1)], cwp[4 * 7 + (e >> 1)], sel);
+        *reinterpret_cast<uint4*>(out + int64_t(o) * p.ld + col_base + jc) = v;
+      }
+    }
+  }
+}
+
+// columns [I, ld) of every output row <- 0 (K padding of the GEMM operand)
+template <typename T>
+__global__ void dequant_zero_pad_kernel(T* out, int64_t ld, int I, int O) {
+  const int o = blockIdx.x;
+  for (int64_t c = I + threadIdx.x; c < ld; c += blockDim.x) out[int64_t(o) * ld + c] = DT<T>::from_float(0.f);
+}
+
 template <typename T>
 int launch_v(const DequantParams& p, int v, cudaStream_t stream) {
   const int ncols = p.quant_order ? int(p.ld) : p.I;
@@ -202,8 +314,35 @@ int dequant_quant_order_launch(const vptq_linear_desc& d, void* wq_out, int64_t 
   p.outlier_idx = p.S ? d.outlier_indices : nullptr;
   p.outlier_cb = p.S ? d.outlier_centroids : nullptr;
   p.out = wq_out, p.ld = ld, p.quant_order = 1;
-  return d.dtype == VPTQ_FP16 ? launch_v<__half>(p, d.vector_len, stream)
-                              : launch_v<__nv_bfloat16>(p, d.vector_len, stream);
+  const int b = p.ib + p.rb;
+  const size_t res_rep_bytes = p.rb ? (size_t(1) << p.rb) * 16 * 8 : 0;
+  const bool fast = d.vector_len == 8 && p.S == 0 && (d.group_size % 8) == 0 && (ld % 8) == 0 &&
+                    res_rep_bytes <= 64 * 1024 && (reinterpret_cast<uintptr_t>(wq_out) & 15u) == 0;
+  if (!fast)
+    return d.dtype == VPTQ_FP16 ? launch_v<__half>(p, d.vector_len, stream)
+                                : launch_v<__nv_bfloat16>(p, d.vector_len, stream);
+  const uint32_t row_words = (uint32_t(DQ_COLS) * b + 31) / 32 + 4;
+  const size_t smem = ((size_t(DQ_ROWS) * row_words * 4 + 127) & ~size_t(127)) + res_rep_bytes;
+  dim3 grid(unsigned(d.num_codebooks * ((d.group_size + DQ_COLS - 1) / DQ_COLS)), unsigned((p.Ro + DQ_ROWS - 1) / DQ_ROWS));
+  if (d.dtype == VPTQ_FP16) {
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(dequant_q8_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); });
+    dequant_q8_kernel<__half><<<grid, DQ_THREADS, smem, stream>>>(p);
+    if (ld > d.in_features)
+      dequant_zero_pad_kernel<__half><<<d.out_features, 64, 0, stream>>>(reinterpret_cast<__half*>(wq_out), ld, d.in_features, d.out_features);
+  } else {
+    static std::once_flag once;
+    std::call_once(once, [] { cudaFuncSetAttribute(dequant_q8_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); });
+    dequant_q8_kernel<__nv_bfloat16><<<grid, DQ_THREADS, smem, stream>>>(p);
+    if (ld > d.in_features)
+      dequant_zero_pad_kernel<__nv_bfloat16><<<d.out_features, 64, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(wq_out), ld, d.in_features, d.out_features);
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("dequant (quantised order) launch: %s", cudaGetErrorString(e));
+    return VPTQ_ERR_CUDA;
+  }
+  return 0;
 }
 
 }  // namespace vptq_b200

@@ -13,11 +13,13 @@
 // Three kernels on the caller's stream:
 //   1. prefill_prep_x     x -> x' (16 bit, quantised column order) and rowbias (fp32)
 //   2. dequant (dequant.cu, quantised-order mode)  packed indices -> Wq tile source [O][Ipad]
-//   3. gemm_tn_tcgen05    warp-specialised: TMA producer / single-thread MMA issuer / 4 epilogue warps,
-//                         128x128x64 tiles, 6-stage smem ring, fp32 accumulator in 128 TMEM columns,
-//                         epilogue adds rowbias[t] + bias[o] and writes 16-bit y.
+//   3. gemm_tn_tcgen05    persistent, warp-specialised: TMA producer / single-thread MMA issuer /
+//                         4 epilogue warps; 128x256x64 tiles, 4-stage smem ring (48 KB per stage), two
+//                         fp32 accumulators in TMEM (2 x 256 columns) so the epilogue of one tile
+//                         (adds rowbias[t] + bias[o], writes 16-bit y) overlaps the MMAs of the next.
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -30,11 +32,12 @@ int dequant_quant_order_launch(const vptq_linear_desc& d, void* wq_out, int64_t 
 
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 64;  // CTA tile: tokens x outputs x reduction
+constexpr int BM = 128, BN = 256, BK = 64;  // CTA tile: tokens x outputs x reduction
 constexpr int UMMA_K = 16;                  // K per tcgen05.mma for 16-bit inputs
-constexpr int STAGES = 6;
+constexpr int STAGES = 4;
 constexpr int TILE_A_BYTES = BM * BK * 2, TILE_B_BYTES = BN * BK * 2;
-constexpr int TMEM_COLS = 128;              // fp32 accumulator: 128 lanes x 128 columns
+constexpr int ACC_STAGES = 2;               // accumulators in flight: epilogue of tile i overlaps the MMAs of tile i+1
+constexpr int TMEM_COLS = ACC_STAGES * BN;  // fp32 accumulators: 128 lanes x (2 x 256) columns = all of TMEM
 constexpr int GEMM_THREADS = 192;           // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
 constexpr int GEMM_SMEM = STAGES * (TILE_A_BYTES + TILE_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
 
@@ -161,16 +164,20 @@ gemm_tn_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   uint8_t* sb = smem + STAGES * TILE_A_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (TILE_A_BYTES + TILE_B_BYTES));
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* acc_full = empty + STAGES;        // MMA -> epilogue: accumulator a is complete
+  uint64_t* acc_empty = acc_full + ACC_STAGES;  // epilogue -> MMA: accumulator a has been drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACC_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int nkb = (p.K + BK - 1) / BK;
+  // persistent CTAs walk the tile list with stride gridDim.x; tokens (m) vary fastest so that the
+  // CTAs running at the same time share the same weight (B) tiles in L2
+  const int tiles_m = (p.T + BM - 1) / BM, tiles_n = (p.O + BN - 1) / BN;
+  const int ntiles = tiles_m * tiles_n;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) mbar_init(&full[s], 1), mbar_init(&empty[s], 1);
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < ACC_STAGES; ++a) mbar_init(&acc_full[a], 1), mbar_init(&acc_empty[a], 4);  // 4 epilogue warps
     fence_mbar_init();
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -184,70 +191,89 @@ gemm_tn_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant
   if (warp == 0) {
     // ===== TMA producer (one lane) =====
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&empty[s], ((kb / STAGES) & 1) ^ 1);  // slot free (passes immediately in round 0)
-        mbar_arrive_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
-        tma_load_2d(sa + s * TILE_A_BYTES, &map_a, kb * BK, m0, &full[s]);
-        tma_load_2d(sb + s * TILE_B_BYTES, &map_b, kb * BK, n0, &full[s]);
+      int it = 0;  // running k-block counter across tiles: slot = it % STAGES, round = it / STAGES
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);  // slot free (passes immediately in round 0)
+          mbar_arrive_expect_tx(&full[s], TILE_A_BYTES + TILE_B_BYTES);
+          tma_load_2d(sa + s * TILE_A_BYTES, &map_a, kb * BK, m0, &full[s]);
+          tma_load_2d(sb + s * TILE_B_BYTES, &map_b, kb * BK, n0, &full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer (one lane issues for the whole CTA) =====
     if (lane == 0) {
       const uint32_t idesc = umma_idesc(p.is_bf16, BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&full[s], (kb / STAGES) & 1);  // TMA bytes have landed
+      int it = 0, nt = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt) {
+        const int a = nt % ACC_STAGES;
+        mbar_wait(&acc_empty[a], ((nt / ACC_STAGES) & 1) ^ 1);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t da = umma_desc_k_sw128(smem_u32(sa + s * TILE_A_BYTES));
-        const uint64_t db = umma_desc_k_sw128(smem_u32(sb + s * TILE_B_BYTES));
+        const uint32_t d_tmem = tmem_base + uint32_t(a * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);  // TMA bytes have landed
+          tc_fence_after();
+          const uint64_t da = umma_desc_k_sw128(smem_u32(sa + s * TILE_A_BYTES));
+          const uint64_t db = umma_desc_k_sw128(smem_u32(sb + s * TILE_B_BYTES));
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in 16-byte units
-          umma_f16_ss(tmem_base, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 16 elements (32 bytes) along K inside the 128-byte swizzle atom: +2 in 16-byte units
+            umma_f16_ss(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);  // frees this smem slot once the MMAs above have read it
         }
-        umma_commit(&empty[s]);  // frees this smem slot once the MMAs above have read it
+        umma_commit(&acc_full[a]);  // accumulator complete
       }
-      umma_commit(tmem_full);  // accumulator complete
     }
   } else {
     // ===== epilogue: TMEM -> registers -> (+rowbias +bias) -> 16-bit y =====
     const int quarter = warp & 3;  // TMEM lanes [32*quarter, 32*quarter+32) belong to this warp
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    const int m = m0 + quarter * 32 + lane;
-    const float rb = m < p.T ? p.rowbias[m] : 0.f;
     const T* bias = reinterpret_cast<const T*>(p.bias);
-    T* yrow = reinterpret_cast<T*>(p.y) + int64_t(m) * p.y_stride;
+    int nt = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++nt) {
+      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      const int a = nt % ACC_STAGES;
+      mbar_wait(&acc_full[a], (nt / ACC_STAGES) & 1);
+      tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const float rb = m < p.T ? p.rowbias[m] : 0.f;
+      T* yrow = reinterpret_cast<T*>(p.y) + int64_t(m) * p.y_stride;
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c0), r);
-      tmem_ld_wait();
-      if (m < p.T) {
-        const int nb = n0 + c0;
-        if (nb + 32 <= p.O && (p.y_stride & 7) == 0 && (nb & 7) == 0) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(a * BN + c0), r);
+        tmem_ld_wait();
+        if (m < p.T) {
+          const int nb = n0 + c0;
+          if (nb + 32 <= p.O && (p.y_stride & 7) == 0) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t w[4];
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t w[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n = nb + j + 2 * i;
-              const float b0 = bias ? DT<T>::to_float(bias[n]) : 0.f, b1 = bias ? DT<T>::to_float(bias[n + 1]) : 0.f;
-              w[i] = DT<T>::pack2(__uint_as_float(r[j + 2 * i]) + rb + b0, __uint_as_float(r[j + 2 * i + 1]) + rb + b1);
+              for (int i = 0; i < 4; ++i) {
+                const int n = nb + j + 2 * i;
+                const float b0 = bias ? DT<T>::to_float(bias[n]) : 0.f, b1 = bias ? DT<T>::to_float(bias[n + 1]) : 0.f;
+                w[i] = DT<T>::pack2(__uint_as_float(r[j + 2 * i]) + rb + b0, __uint_as_float(r[j + 2 * i + 1]) + rb + b1);
+              }
+              *reinterpret_cast<uint4*>(yrow + nb + j) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            *reinterpret_cast<uint4*>(yrow + nb + j) = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-        } else {
-          for (int j = 0; j < 32; ++j) {
-            const int n = nb + j;
-            if (n < p.O) yrow[n] = DT<T>::from_float(__uint_as_float(r[j]) + rb + (bias ? DT<T>::to_float(bias[n]) : 0.f));
+          } else {
+            for (int j = 0; j < 32; ++j) {
+              const int n = nb + j;
+              if (n < p.O) yrow[n] = DT<T>::from_float(__uint_as_float(r[j]) + rb + (bias ? DT<T>::to_float(bias[n]) : 0.f));
+            }
           }
         }
       }
+      // this warp is done reading accumulator a: hand it back to the MMA issuer
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[a]);
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
@@ -275,8 +301,8 @@ EncodeTiledFn encode_tiled() {
   return fn;
 }
 
-// row-major [rows][cols] 16-bit matrix, row pitch `ld` elements; box = 64 columns x 128 rows, 128B swizzle
-int make_map(CUtensorMap* m, int is_bf16, const void* base, int64_t rows, int64_t cols, int64_t ld) {
+// row-major [rows][cols] 16-bit matrix, row pitch `ld` elements; box = 64 columns x box_rows rows, 128B swizzle
+int make_map(CUtensorMap* m, int is_bf16, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn enc = encode_tiled();
   if (!enc) {
     set_error("quant_gemm: cuTensorMapEncodeTiled not available from the driver");
@@ -284,7 +310,7 @@ int make_map(CUtensorMap* m, int is_bf16, const void* base, int64_t rows, int64_
   }
   cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
   cuuint64_t strides[1] = {cuuint64_t(ld) * 2};
-  cuuint32_t box[2] = {BK, BM};
+  cuuint32_t box[2] = {BK, cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -349,12 +375,15 @@ int gemm_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
   if (int rc = dequant_quant_order_launch(d, wq, w.kpad, stream)) return rc;
   // 3. tensor-core GEMM
   CUtensorMap map_a, map_b;
-  if (int rc = make_map(&map_a, is_bf16, xq, tokens, w.kpad, w.kpad)) return rc;
-  if (int rc = make_map(&map_b, is_bf16, wq, d.out_features, w.kpad, w.kpad)) return rc;
+  if (int rc = make_map(&map_a, is_bf16, xq, tokens, w.kpad, w.kpad, BM)) return rc;
+  if (int rc = make_map(&map_b, is_bf16, wq, d.out_features, w.kpad, w.kpad, BN)) return rc;
   GemmParams p{};
   p.bias = d.bias, p.rowbias = rowbias, p.y = y, p.y_stride = y_stride;
   p.T = tokens, p.O = d.out_features, p.K = int(w.kpad), p.is_bf16 = is_bf16;
-  dim3 grid(unsigned((d.out_features + BN - 1) / BN), unsigned((tokens + BM - 1) / BM));
+  const DeviceInfo* dev = device_info();
+  if (!dev) return VPTQ_ERR_CUDA;
+  const int ntiles = ((d.out_features + BN - 1) / BN) * ((tokens + BM - 1) / BM);
+  dim3 grid(unsigned(std::min(ntiles, dev->sm_count)));  // persistent: one CTA per SM
   cudaError_t e;
   if (is_bf16) {
     std::call_once(g_attr_once[1], [] {
