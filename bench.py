@@ -182,10 +182,17 @@ def make_step(m, stack, device, dtype, rank, world, flags):
     return x_in, step, launches
 
 
+def _log(msg):
+    if os.environ.get("BENCH_VERBOSE"):
+        print(f"[bench r{os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
+    import faulthandler
     import torch
     import torch.distributed as dist
     from vptq_b200 import native
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "900")), exit=True)  # a hang leaves a trace
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,6 +204,7 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
+    _log("process group up")
     native.lib()
     dtype = torch.float16
     m, q = dict(LLAMA3_8B), QUANT
@@ -205,6 +213,7 @@ def run_ours(args):
     flags = 0 if args.no_pdl else native.FLAG_PDL
 
     stack = build_stack(m, q, device, rank, world, dtype)
+    _log("weights built")
     x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags)
     x_host = torch.randn(1, m["hidden"]).to(dtype).pin_memory()
     y_host = torch.empty(1, m["hidden"], dtype=dtype).pin_memory()
@@ -216,10 +225,20 @@ def run_ours(args):
         for _ in range(2):                      # eager warm-up: smem attributes, workspace, NCCL channels
             h_out = step()
         s.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=s):
-            h_out = step()
+        _log("eager warm-up done")
+        use_graph = not args.tp_eager or world == 1
+        if use_graph:
+            graph = torch.cuda.CUDAGraph()
+            # thread_local: the NCCL watchdog thread may touch CUDA while this thread captures
+            with torch.cuda.graph(graph, stream=s, capture_error_mode="thread_local"):
+                h_out = step()
+            replay = graph.replay
+        else:
+            def replay():
+                nonlocal h_out
+                h_out = step()
         n_launch = launches[0]
+        _log("graph captured" if use_graph else "eager mode")
 
         def barrier():
             if world > 1:
@@ -228,8 +247,9 @@ def run_ours(args):
 
         # ---- `value`: device-resident, W warm-up + K timed graph replays -------------------------
         for _ in range(max(args.warmup, 3)):
-            graph.replay()
+            replay()
         barrier()
+        _log("warm-up replays done")
         clocks = ClockSampler(local)
         if rank == 0:
             clocks.start()
@@ -237,7 +257,7 @@ def run_ours(args):
         barrier()
         ev[0].record(s)
         for _ in range(args.steps):
-            graph.replay()
+            replay()
         ev[1].record(s)
         barrier()
         ms = ev[0].elapsed_time(ev[1])
@@ -247,20 +267,21 @@ def run_ours(args):
         # ---- `e2e`: host buffers, H2D + D2H inside the timed region, per-step sync ------------------
         e2e_steps = args.steps
         for _ in range(3):
-            x_in.copy_(x_host, non_blocking=True); graph.replay(); y_host.copy_(h_out, non_blocking=True); s.synchronize()
+            x_in.copy_(x_host, non_blocking=True); replay(); y_host.copy_(h_out, non_blocking=True); s.synchronize()
         barrier()
         ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
         t0 = time.perf_counter()
         ev2[0].record(s)
         for _ in range(e2e_steps):
             x_in.copy_(x_host, non_blocking=True)
-            graph.replay()
+            replay()
             y_host.copy_(h_out, non_blocking=True)
             s.synchronize()
         ev2[1].record(s)
         barrier()
         ms_e2e = ev2[0].elapsed_time(ev2[1])
         wall_e2e = (time.perf_counter() - t0) * 1e3
+    _log("timed regions done")
 
     if world > 1:
         tms = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
@@ -292,7 +313,8 @@ def run_ours(args):
                                    "attention/norm/lm_head not on the VPTQ path and not executed",
                        "parallelism": f"tp{world} (out_features sharded, 1 NCCL all-reduce per linear)" if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2: 2.6 GB of distinct packed indices streamed per step",
-                       "launch": "one CUDA graph per token, PDL " + ("off" if args.no_pdl else "on")},
+                       "launch": ("one CUDA graph per token" if use_graph else "eager launches") +
+                                 ", PDL " + ("off" if (args.no_pdl or world > 1) else "on")},
             "gpu_launches": n_launch * args.steps,
             "e2e": {"value": round(1e3 / (ms_e2e / e2e_steps), 2), "unit": "tokens/s",
                     "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2,
@@ -308,6 +330,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(m, q, budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
+    faulthandler.cancel_dump_traceback_later()
     if world > 1:
         dist.destroy_process_group()
 
@@ -375,6 +398,7 @@ def main():
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--tp-eager", action="store_true", help="N > 1: launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--debug-layers", type=int, default=0, help="debugging only: truncate the model (invalid as a result)")
     args = ap.parse_args()
     if args.impl == "reference":
