@@ -332,7 +332,12 @@ def run_ours(args):
         print(json.dumps(line), flush=True)
     faulthandler.cancel_dump_traceback_later()
     if world > 1:
-        dist.destroy_process_group()
+        # tearing down a process group whose collectives live in a captured CUDA graph can block
+        # forever; every rank has its result out, so leave without the destructor chain
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------
