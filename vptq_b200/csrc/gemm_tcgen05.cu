@@ -44,30 +44,94 @@ constexpr int GEMM_SMEM = STAGES * (TILE_A_BYTES + TILE_B_BYTES) + 1024 /*align*
 // ---------------------------------------------------------------------------------------------
 // x' = x[perm] * scale[perm]  and  rowbias = x . wbias
 // ---------------------------------------------------------------------------------------------
+// One CTA per token: the row of x is staged in shared memory with coalesced 16-byte loads, then
+// gathered from there (2-byte shared-memory reads) while perm / scale stream in coalesced, and x' is
+// written with 16-byte stores.  `scale_q` is the optional quantised-order copy scale[perm[c]]
+// (vptq_linear_desc.weight_scale_q); without it scale is gathered through perm.
 template <typename T>
 __global__ void __launch_bounds__(256) prefill_prep_x(const T* __restrict__ x, int64_t x_stride,
                                                       const uint16_t* __restrict__ perm,
-                                                      const T* __restrict__ scale, const T* __restrict__ wbias,
-                                                      T* __restrict__ xq, int64_t xq_stride,
-                                                      float* __restrict__ rowbias, int I) {
-  const int t = blockIdx.x;
+                                                      const T* __restrict__ scale, const T* __restrict__ scale_q,
+                                                      const T* __restrict__ wbias, T* __restrict__ xq,
+                                                      int64_t xq_stride, float* __restrict__ rowbias, int I) {
+  extern __shared__ __align__(16) uint8_t prep_smem[];
+  T* sx = reinterpret_cast<T*>(prep_smem);
+  const int t = blockIdx.x, tid = threadIdx.x;
   const T* xr = x + int64_t(t) * x_stride;
   T* out = xq + int64_t(t) * xq_stride;
   float bs = 0.f;
-  for (int c = threadIdx.x; c < I; c += blockDim.x) {
-    const int f = perm ? int(perm[c]) : c;
-    const float xv = DT<T>::to_float(xr[f]);
-    out[c] = DT<T>::from_float(scale ? xv * DT<T>::to_float(scale[f]) : xv);
-    if (wbias) bs = fmaf(xv, DT<T>::to_float(wbias[f]), bs);
+  const bool vec = ((reinterpret_cast<uintptr_t>(xr) & 15u) == 0) && ((I & 7) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(wbias) & 15u) == 0);
+  if (vec) {
+    for (int i = tid * 8; i < I; i += 256 * 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(xr + i);
+      *reinterpret_cast<uint4*>(sx + i) = v;
+      if (wbias) {
+        const uint4 w = *reinterpret_cast<const uint4*>(wbias + i);
+        const uint32_t* vp = reinterpret_cast<const uint32_t*>(&v);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(&w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = DT<T>::unpack2(vp[k]), c = DT<T>::unpack2(wp[k]);
+          bs = fmaf(a.x, c.x, fmaf(a.y, c.y, bs));
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < I; i += 256) {
+      sx[i] = xr[i];
+      if (wbias) bs = fmaf(DT<T>::to_float(xr[i]), DT<T>::to_float(wbias[i]), bs);
+    }
   }
-  for (int c = I + threadIdx.x; c < xq_stride; c += blockDim.x) out[c] = DT<T>::from_float(0.f);  // K padding
+  __syncthreads();
+  const bool vec_out = ((I & 7) == 0) && (!perm || (reinterpret_cast<uintptr_t>(perm) & 15u) == 0) &&
+                       (!scale_q || (reinterpret_cast<uintptr_t>(scale_q) & 15u) == 0) && ((xq_stride & 7) == 0);
+  if (vec_out) {
+    for (int c = tid * 8; c < I; c += 256 * 8) {
+      uint32_t pc[8];
+      if (perm) {
+        const uint4 pv = *reinterpret_cast<const uint4*>(perm + c);
+        const uint32_t* pp = reinterpret_cast<const uint32_t*>(&pv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) pc[2 * k] = pp[k] & 0xffffu, pc[2 * k + 1] = pp[k] >> 16;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) pc[k] = uint32_t(c + k);
+      }
+      float sc[8];
+      if (scale_q) {
+        const uint4 sv = *reinterpret_cast<const uint4*>(scale_q + c);
+        const uint32_t* sp = reinterpret_cast<const uint32_t*>(&sv);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f2 = DT<T>::unpack2(sp[k]);
+          sc[2 * k] = f2.x, sc[2 * k + 1] = f2.y;
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sc[k] = scale ? DT<T>::to_float(scale[pc[k]]) : 1.f;
+      }
+      uint32_t w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        w[k] = DT<T>::pack2(DT<T>::to_float(sx[pc[2 * k]]) * sc[2 * k], DT<T>::to_float(sx[pc[2 * k + 1]]) * sc[2 * k + 1]);
+      *reinterpret_cast<uint4*>(out + c) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  } else {
+    for (int c = tid; c < I; c += 256) {
+      const int f = perm ? int(perm[c]) : c;
+      const float sc = scale_q ? DT<T>::to_float(scale_q[c]) : (scale ? DT<T>::to_float(scale[f]) : 1.f);
+      out[c] = DT<T>::from_float(DT<T>::to_float(sx[f]) * sc);
+    }
+  }
+  for (int c = I + tid; c < xq_stride; c += 256) out[c] = DT<T>::from_float(0.f);  // K padding
   __shared__ float red[8];
   bs = warp_sum(bs);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = bs;
+  if ((tid & 31) == 0) red[tid >> 5] = bs;
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     float v = 0.f;
-    for (int w = 0; w < int(blockDim.x >> 5); ++w) v += red[w];
+    for (int w = 0; w < 8; ++w) v += red[w];
     rowbias[t] = v;
   }
 }
@@ -341,7 +405,7 @@ GemmWorkspace gemm_layout(const vptq_linear_desc& d, int tokens) {
   return w;
 }
 
-std::once_flag g_attr_once[2];
+std::once_flag g_attr_once[2], g_prep_once;
 
 }  // namespace
 
@@ -361,16 +425,22 @@ int gemm_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
   const int is_bf16 = d.dtype == VPTQ_BF16;
 
   // 1. x' and rowbias
+  const size_t prep_smem = align_up(size_t(d.in_features) * 2, 16);
+  std::call_once(g_prep_once, [] {
+    cudaFuncSetAttribute(prefill_prep_x<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
+    cudaFuncSetAttribute(prefill_prep_x<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
+  });
   if (is_bf16)
-    prefill_prep_x<__nv_bfloat16><<<tokens, 256, 0, stream>>>(
+    prefill_prep_x<__nv_bfloat16><<<tokens, 256, prep_smem, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), x_stride, d.perm,
-        reinterpret_cast<const __nv_bfloat16*>(d.weight_scale), reinterpret_cast<const __nv_bfloat16*>(d.weight_bias),
-        reinterpret_cast<__nv_bfloat16*>(xq), w.kpad, rowbias, d.in_features);
-  else
-    prefill_prep_x<__half><<<tokens, 256, 0, stream>>>(
-        reinterpret_cast<const __half*>(x), x_stride, d.perm, reinterpret_cast<const __half*>(d.weight_scale),
-        reinterpret_cast<const __half*>(d.weight_bias), reinterpret_cast<__half*>(xq), w.kpad, rowbias,
+        reinterpret_cast<const __nv_bfloat16*>(d.weight_scale), reinterpret_cast<const __nv_bfloat16*>(d.weight_scale_q),
+        reinterpret_cast<const __nv_bfloat16*>(d.weight_bias), reinterpret_cast<__nv_bfloat16*>(xq), w.kpad, rowbias,
         d.in_features);
+  else
+    prefill_prep_x<__half><<<tokens, 256, prep_smem, stream>>>(
+        reinterpret_cast<const __half*>(x), x_stride, d.perm, reinterpret_cast<const __half*>(d.weight_scale),
+        reinterpret_cast<const __half*>(d.weight_scale_q), reinterpret_cast<const __half*>(d.weight_bias),
+        reinterpret_cast<__half*>(xq), w.kpad, rowbias, d.in_features);
   // 2. Wq in quantised column order (no scale / bias / perm)
   if (int rc = dequant_quant_order_launch(d, wq, w.kpad, stream)) return rc;
   // 3. tensor-core GEMM
