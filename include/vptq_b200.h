@@ -148,6 +148,17 @@ VPTQ_B200_API int vptq_b200_quant_gemv(const vptq_linear_desc* desc, const void*
                          size_t workspace_bytes, uint32_t flags, void* stream);
 
 /*
+ * Decode path, horizontally fused: up to 4 layers that read the SAME x (q/k/v, gate/up of a
+ * decoder layer) in ONE launch -- y_l = x W_l^T + bias_l for every l.  No reference counterpart
+ * (the reference launches each VQuantLinear separately); identical results to n separate
+ * vptq_b200_quant_gemv calls.  tokens <= 2, vector_len 8.  Returns VPTQ_ERR_UNSUPPORTED when the
+ * layers do not admit one launch configuration: the caller then launches them one by one.
+ */
+VPTQ_B200_API int vptq_b200_quant_gemv_multi(int32_t n, const vptq_linear_desc* const* descs, const void* x,
+                                             int64_t x_stride, void* const* ys, const int64_t* y_strides,
+                                             int32_t tokens, uint32_t flags, void* stream);
+
+/*
  * W[o][f] (row-major [O][I], `dtype`), scale/bias/perm applied -- what the reference's dequant
  * returns (csrc/dequant.cu:227-287, Return_OUF_x_INF=true; python spec
  * vptq/ops/quant_gemm.py:43-158).

@@ -188,6 +188,22 @@ int vptq_b200_quant_gemv(const vptq_linear_desc* desc, const void* x, int64_t x_
                      static_cast<cudaStream_t>(stream));
 }
 
+int vptq_b200_quant_gemv_multi(int32_t n, const vptq_linear_desc* const* descs, const void* x, int64_t x_stride,
+                               void* const* ys, const int64_t* y_strides, int32_t tokens, uint32_t flags, void* stream) {
+  if (!descs || !x || !ys || !y_strides || n < 1) {
+    set_error("quant_gemv_multi: NULL argument");
+    return VPTQ_ERR_INVALID;
+  }
+  for (int l = 0; l < n; ++l) {
+    if (int rc = validate(descs[l], l == 0)) return rc;
+    if (!ys[l] || y_strides[l] < descs[l]->out_features || x_stride < descs[l]->in_features) {
+      set_error("quant_gemv_multi: bad y / stride for layer %d", l);
+      return VPTQ_ERR_INVALID;
+    }
+  }
+  return gemv_multi_launch(n, descs, x, x_stride, ys, y_strides, tokens, flags, static_cast<cudaStream_t>(stream));
+}
+
 int vptq_b200_dequant(const vptq_linear_desc* desc, void* w_out, void* workspace, size_t workspace_bytes,
                       void* stream) {
   if (int rc = validate(desc, true)) return rc;

@@ -94,7 +94,8 @@ int max_active_clusters(const void* fn, int csize, int threads, int smem, int op
 static unsigned long long* g_prof_buffer = nullptr;
 void gemv_set_profile_buffer(void* dev_ptr) { g_prof_buffer = static_cast<unsigned long long*>(dev_ptr); }
 
-int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev, GemvPlan* out) {
+int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev, GemvPlan* out, int slots_override,
+                   int force_cpg) {
   const int v = d.vector_len, G = d.num_codebooks, gs = d.group_size;
   const int Ro = (d.out_features + v - 1) / v;
   const int ib = ilog2(d.num_centroids);
@@ -122,7 +123,9 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
   const int res_rep_want = tn.rep >= 0 ? (tn.rep ? 8 : 1) : 8;
   const int res_rep_max = (rb && v == 8 && res_bytes * 8 <= 32768) ? res_rep_want : 1;
   const int smem_limit = dev.smem_optin - kSmemReserve;
-  const int slots = sms;  // one CTA per SM: the whole register file and shared memory feed one pipeline
+  // one CTA per SM: the whole register file and shared memory feed one pipeline; a fused launch
+  // gives every layer its share of the SMs
+  const int slots = slots_override > 0 ? std::min(slots_override, sms) : sms;
 
   // One attempt = (warps per CTA, main codebook in shared memory?).  First fit wins.
   struct Attempt { int warps; bool main_smem; };
@@ -142,6 +145,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
     double best_cost = 1e300;
     for (int cpg = 1; cpg <= 64; cpg *= 2) {
       if (tn.cpg && cpg != tn.cpg) continue;
+      if (force_cpg && cpg != force_cpg) continue;
       const int cc = int(align_up(size_t((gs + cpg - 1) / cpg), 128));
       if (cc > kMaxChunkCols) continue;
       if (cpg > 1 && cc < 256) break;
@@ -267,23 +271,11 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
   return VPTQ_ERR_UNSUPPORTED;
 }
 
-int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void* y, int64_t y_stride,
-                int tokens, void* workspace, size_t workspace_bytes, uint32_t flags, cudaStream_t stream) {
-  const DeviceInfo* dev = device_info();
-  if (!dev) return VPTQ_ERR_CUDA;
-  if (!supported_vec_len(d.vector_len)) {
-    set_error("gemv: vector_len %d not supported (2,4,6,8,10,12,16)", d.vector_len);
-    return VPTQ_ERR_UNSUPPORTED;
-  }
-  GemvPlan pl;
-  if (int rc = gemv_make_plan(d, tokens, *dev, &pl)) return rc;
-  const size_t need = pl.ws_partials_bytes ? pl.ws_counters_bytes + pl.ws_partials_bytes : 0;
-  if (need && (workspace_bytes < need || !workspace)) {
-    set_error("gemv: workspace %zu bytes < required %zu", workspace_bytes, need);
-    return VPTQ_ERR_WORKSPACE;
-  }
+namespace {
 
-  GemvParams p{};
+void fill_params(GemvParams& p, const vptq_linear_desc& d, const GemvPlan& pl, int64_t x_stride, int64_t y_stride,
+                 void* workspace) {
+  p = GemvParams{};
   p.indices = reinterpret_cast<const uint32_t*>(d.indices);
   p.idx_stride_g = d.index_stride_codebook;
   p.idx_stride_r = d.index_stride_row;
@@ -318,7 +310,59 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
                      : 0;
   p.prof = g_prof_buffer;
   p.plan = pl;
+}
 
+template <typename Fn, typename Params>
+int launch(Fn fn, const Params& params, int grid, int threads, uint32_t smem, int cluster, uint32_t flags,
+           cudaStream_t stream) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(grid));
+  cfg.blockDim = dim3(unsigned(threads));
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int nattr = 0;
+  if (flags & VPTQ_FLAG_PDL) {
+    attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+    ++nattr;
+  }
+  if (cluster > 1) {
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = unsigned(cluster);
+    attr[nattr].val.clusterDim.y = 1;
+    attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = unsigned(nattr);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, fn, params);
+  if (e != cudaSuccess) {
+    set_error("gemv launch (grid=%d block=%d smem=%u cluster=%d): %s", grid, threads, smem, cluster, cudaGetErrorString(e));
+    return VPTQ_ERR_CUDA;
+  }
+  return 0;
+}
+
+}  // namespace
+
+int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void* y, int64_t y_stride,
+                int tokens, void* workspace, size_t workspace_bytes, uint32_t flags, cudaStream_t stream) {
+  const DeviceInfo* dev = device_info();
+  if (!dev) return VPTQ_ERR_CUDA;
+  if (!supported_vec_len(d.vector_len)) {
+    set_error("gemv: vector_len %d not supported (2,4,6,8,10,12,16)", d.vector_len);
+    return VPTQ_ERR_UNSUPPORTED;
+  }
+  GemvPlan pl;
+  if (int rc = gemv_make_plan(d, tokens, *dev, &pl)) return rc;
+  const size_t need = pl.ws_partials_bytes ? pl.ws_counters_bytes + pl.ws_partials_bytes : 0;
+  if (need && (workspace_bytes < need || !workspace)) {
+    set_error("gemv: workspace %zu bytes < required %zu", workspace_bytes, need);
+    return VPTQ_ERR_WORKSPACE;
+  }
+  GemvParams p;
+  fill_params(p, d, pl, x_stride, y_stride, workspace);
   const size_t esz = 2;
   for (int t0 = 0; t0 < tokens;) {
     int nt = pl.nt;
@@ -333,36 +377,93 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
     p.y = reinterpret_cast<uint8_t*>(y) + size_t(t0) * y_stride * esz;
     // the carve-up was sized for pl.nt tokens; a narrower tail pass fits a fortiori (the kernel's
     // partial-sum indexing uses its own template NT consistently on both sides)
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(unsigned(pl.grid));
-    cfg.blockDim = dim3(unsigned(pl.threads));
-    cfg.dynamicSmemBytes = pl.smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    int nattr = 0;
-    if (flags & VPTQ_FLAG_PDL) {
-      attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[nattr].val.programmaticStreamSerializationAllowed = 1;
-      ++nattr;
-    }
-    if (pl.cluster) {
-      attr[nattr].id = cudaLaunchAttributeClusterDimension;
-      attr[nattr].val.clusterDim.x = unsigned(pl.nch);
-      attr[nattr].val.clusterDim.y = 1;
-      attr[nattr].val.clusterDim.z = 1;
-      ++nattr;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = unsigned(nattr);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, fn, p);
-    if (e != cudaSuccess) {
-      set_error("gemv launch (grid=%d block=%d smem=%u cluster=%d): %s", pl.grid, pl.threads, pl.smem_bytes,
-                pl.cluster ? pl.nch : 1, cudaGetErrorString(e));
-      return VPTQ_ERR_CUDA;
-    }
+    if (int rc = launch(fn, p, pl.grid, pl.threads, pl.smem_bytes, pl.cluster ? pl.nch : 1, flags, stream)) return rc;
     t0 += nt;
   }
   return 0;
+}
+
+// Several layers reading the same x in one launch (q/k/v, gate/up).  Every layer gets a share of the
+// SMs proportional to its index volume and is planned for that share; the launch needs one kernel
+// instantiation, one block size and one cluster size for all of them -- otherwise (or when a layer
+// needs the global-memory split-K variant) VPTQ_ERR_UNSUPPORTED tells the caller to launch separately.
+int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x, int64_t x_stride, void* const* ys,
+                      const int64_t* y_strides, int tokens, uint32_t flags, cudaStream_t stream) {
+  const DeviceInfo* dev = device_info();
+  if (!dev) return VPTQ_ERR_CUDA;
+  if (n < 1 || n > kMaxFused || tokens < 1 || tokens > 2) {
+    set_error("gemv_multi: 1..%d layers and 1..2 tokens (got %d layers, %d tokens)", kMaxFused, n, tokens);
+    return VPTQ_ERR_UNSUPPORTED;
+  }
+  const vptq_linear_desc& d0 = *descs[0];
+  double vol[kMaxFused], total = 0;
+  for (int l = 0; l < n; ++l) {
+    const vptq_linear_desc& d = *descs[l];
+    if (d.vector_len != 8 || d.dtype != d0.dtype || d.in_features != d0.in_features ||
+        (d.num_res_centroids > 0) != (d0.num_res_centroids > 0)) {
+      set_error("gemv_multi: layers must share dtype, in_features, vector_len 8 and residual-ness");
+      return VPTQ_ERR_UNSUPPORTED;
+    }
+    vol[l] = double((d.out_features + 7) / 8) * d.in_features;
+    total += vol[l];
+  }
+  // plan the largest layer first: its chunking (cluster size) is imposed on the others
+  int big = 0;
+  for (int l = 1; l < n; ++l)
+    if (vol[l] > vol[big]) big = l;
+  GemvPlan plans[kMaxFused];
+  // 1. provisional plan of the largest layer -> chunking / cluster size for everyone
+  if (int rc = gemv_make_plan(*descs[big], tokens, *dev, &plans[big], std::max(8, int(dev->sm_count * vol[big] / total)), 0))
+    return rc;
+  const int cpg = plans[big].cpg, nch = plans[big].nch;
+  // 2. SMs that can be used at once: all clusters of all layers must be co-resident
+  int avail = dev->sm_count;
+  if (plans[big].cluster) {
+    GemvKernelFn probe = pick_kernel(*descs[big], plans[big].nt, plans[big].main_in_smem != 0);
+    const int nmax = probe ? max_active_clusters(reinterpret_cast<const void*>(probe), nch, plans[big].threads,
+                                                 200 * 1024, dev->smem_optin)
+                           : -1;
+    if (nmax > 0) avail = std::min(avail, nmax * nch);
+  }
+  // 3. shares proportional to index volume, in whole clusters
+  int share[kMaxFused], used = 0;
+  for (int l = 0; l < n; ++l) {
+    share[l] = std::max(nch, int(avail * vol[l] / total) / nch * nch);
+    used += share[l];
+  }
+  while (used > avail && share[big] > nch) share[big] -= nch, used -= nch;
+  if (used > avail) {
+    set_error("gemv_multi: %d layers do not fit %d co-resident CTAs", n, avail);
+    return VPTQ_ERR_UNSUPPORTED;
+  }
+  while (used + nch <= avail) share[big] += nch, used += nch;  // hand the remainder to the largest layer
+  for (int l = 0; l < n; ++l)
+    if (int rc = gemv_make_plan(*descs[l], tokens, *dev, &plans[l], share[l], cpg)) return rc;
+  GemvMultiParams mp{};
+  mp.n = n;
+  uint32_t smem = 0, begin = 0;
+  for (int l = 0; l < n; ++l) {
+    const GemvPlan& pl = plans[l];
+    if (pl.nch != plans[big].nch || pl.threads != plans[big].threads || pl.cluster != plans[big].cluster ||
+        pl.main_in_smem != plans[big].main_in_smem || pl.nt != plans[big].nt || pl.ws_partials_bytes) {
+      set_error("gemv_multi: the layers do not admit one launch configuration");
+      return VPTQ_ERR_UNSUPPORTED;
+    }
+    fill_params(mp.layer[l], *descs[l], pl, x_stride, y_strides[l], nullptr);
+    mp.layer[l].x = x;
+    mp.layer[l].y = ys[l];
+    mp.grid_begin[l] = begin;
+    begin += uint32_t(pl.grid);
+    smem = std::max(smem, pl.smem_bytes);
+  }
+  for (int l = n; l <= kMaxFused; ++l) mp.grid_begin[l] = begin;
+  GemvMultiKernelFn fn = gemv_multi_kernel_v8(d0.dtype, plans[big].nt, plans[big].main_in_smem != 0, d0.num_res_centroids > 0);
+  if (!fn || plans[big].nt != tokens) {
+    set_error("gemv_multi: no fused kernel for this configuration");
+    return VPTQ_ERR_UNSUPPORTED;
+  }
+  if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(fn), dev->smem_optin)) return rc;
+  return launch(fn, mp, int(begin), plans[big].threads, smem, plans[big].cluster ? plans[big].nch : 1, flags, stream);
 }
 
 }  // namespace vptq_b200

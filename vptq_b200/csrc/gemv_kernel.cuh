@@ -113,9 +113,10 @@ __device__ __forceinline__ float warp_reduce_to_lane(float (&acc)[V], int lane) 
   }
 }
 
+// One CTA's share of one layer.  `bidx` / `gdim`: this CTA's index within, and the size of, the
+// layer's own grid (a fused launch concatenates the grids of several layers, see gemv_multi_kernel).
 template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
-__global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+__device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, const uint32_t bidx, const uint32_t gdim) {
   constexpr int U = (NT == 1 && V <= 8) ? 8 : 4;  // independent codebook gathers in flight per lane
   constexpr int EB = 2 * V;                       // bytes per codebook entry
   const GemvPlan& pl = p.plan;
@@ -123,15 +124,15 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   // phase stamps (ns) of thread 0 of the first and of the last CTA: tools/profile_gemv.py --phases
   auto stamp = [&](int slot) {
-    if (p.prof && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+    if (p.prof && tid == 0 && (bidx == 0 || bidx == gdim - 1)) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      p.prof[(blockIdx.x == 0 ? 0 : 16) + slot] = t;
+      p.prof[(bidx == 0 ? 0 : 16) + slot] = t;
     }
   };
   stamp(0);
-  const int chunk = blockIdx.x % pl.nch;  // == %cluster_ctarank when launched as a cluster
-  const int cta_in_chunk = blockIdx.x / pl.nch;
+  const int chunk = bidx % pl.nch;  // == %cluster_ctarank when launched as a cluster
+  const int cta_in_chunk = bidx / pl.nch;
   const int g = chunk / pl.cpg, cig = chunk % pl.cpg;
   const int f0 = cig * pl.chunk_cols;
   const int f1 = min(p.gs, f0 + pl.chunk_cols);
@@ -160,6 +161,32 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   const T* res_g = RES ? reinterpret_cast<const T*>(p.res_centroids) + int64_t(g) * p.rcb_stride : nullptr;
 
   const int nrows_cta = cta_in_chunk < p.Ro ? (p.Ro - cta_in_chunk + pl.cpc - 1) / pl.cpc : 0;
+
+  // -------- first thing: get the x-independent column metadata of this thread's first 4 columns on
+  // their way (perm, scale, wbias come from DRAM once per token: ~1 us that overlaps the setup below)
+  const T* scale = reinterpret_cast<const T*>(p.scale);
+  const T* wbias = reinterpret_cast<const T*>(p.wbias);
+  const T* scale_q = reinterpret_cast<const T*>(p.scale_q);
+  const T* wbias_q = reinterpret_cast<const T*>(p.wbias_q);
+  auto load_cols = [&](int i0, int (&pc)[4], float (&sc)[4], float (&wb)[4]) {
+    int cc[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * int(blockDim.x);
+      const int c = i < ncols ? p.S + g * p.gs + f0 + i : i - ncols;
+      cc[k] = i < n_all ? c : 0;
+      pc[k] = i < n_all ? (p.perm ? int(p.perm[c]) : c) : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // quantised-order copies (built once at load time) cut the perm -> scale dependent-load chain
+      sc[k] = scale_q ? DT<T>::to_float(scale_q[cc[k]]) : (scale ? DT<T>::to_float(scale[pc[k]]) : 1.f);
+      wb[k] = wbias_q ? DT<T>::to_float(wbias_q[cc[k]]) : (wbias ? DT<T>::to_float(wbias[pc[k]]) : 0.f);
+    }
+  };
+  int pc0[4];
+  float sc0[4], wb0[4];
+  load_cols(tid, pc0, sc0, wb0);
 
   // -------- barrier init -----------------------------------------------------------------
   {
@@ -206,14 +233,14 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
     const int st = q % pl.stages;
     uint8_t* dst = ring + st * pl.stage_bytes;
     if (p.idx_tma_ok && (nw & 3) == 0) {
-      if (lane == 0) {
-        fence_proxy_async_smem();
+      if (lane == 0) {  // (the stage was only READ through the generic proxy before: no proxy fence needed)
         mbar_arrive_expect_tx(&full[st], uint32_t(nw) * 4u);
         tma_bulk_g2s(dst, src, uint32_t(nw) * 4u, &full[st], pol_stream);
       }
     } else {  // ragged / unaligned rows: plain word copy by the whole warp
       uint32_t* d32 = reinterpret_cast<uint32_t*>(dst);
       for (int i = lane; i < nw; i += 32) d32[i] = ldg_nc_u32(src + i);
+      fence_proxy_async_smem();  // a later TMA refill of this stage must be ordered after these generic writes
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[st]);
     }
@@ -266,35 +293,24 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   stamp(2);
   // -------- x' prologue, phase A: everything that does not depend on x --------------------
   // four columns per thread and step, loads grouped by dependence level (perm -> scale, wbias)
-  const T* scale = reinterpret_cast<const T*>(p.scale);
-  const T* wbias = reinterpret_cast<const T*>(p.wbias);
-  const T* scale_q = reinterpret_cast<const T*>(p.scale_q);
-  const T* wbias_q = reinterpret_cast<const T*>(p.wbias_q);
   // the 1 MiB codebook of an L2-gather layer is cold (2.6 GB of other layers went through the L2
   // since its last use): pull this CTA's slice of it towards L2 while the prologue runs
   if constexpr (!MAIN_SMEM) {
     if (tid == 32) {
       const uint32_t total_b = uint32_t(p.K) * EB;
-      const uint32_t slice = ((total_b + gridDim.x - 1) / gridDim.x + 15u) & ~15u;
-      const uint32_t off = blockIdx.x * slice;
+      const uint32_t slice = ((total_b + gdim - 1) / gdim + 15u) & ~15u;
+      const uint32_t off = bidx * slice;
       if (off < total_b) l2_prefetch_bulk(reinterpret_cast<const uint8_t*>(cent_g) + off, min(slice, total_b - off));
     }
   }
   for (int i0 = tid; i0 < n_all; i0 += 4 * blockDim.x) {
-    int pc[4], cc[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * blockDim.x;
-      const int c = i < ncols ? p.S + g * p.gs + f0 + i : i - ncols;
-      cc[k] = i < n_all ? c : 0;
-      pc[k] = i < n_all ? (p.perm ? int(p.perm[c]) : c) : 0;
-    }
+    int pc[4];
     float sc[4], wb[4];
+    if (i0 == tid) {  // the batch whose loads were issued at kernel entry
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      // quantised-order copies (built once at load time) cut the perm -> scale dependent-load chain
-      sc[k] = scale_q ? DT<T>::to_float(scale_q[cc[k]]) : (scale ? DT<T>::to_float(scale[pc[k]]) : 1.f);
-      wb[k] = wbias_q ? DT<T>::to_float(wbias_q[cc[k]]) : (wbias ? DT<T>::to_float(wbias[pc[k]]) : 0.f);
+      for (int k = 0; k < 4; ++k) pc[k] = pc0[k], sc[k] = sc0[k], wb[k] = wb0[k];
+    } else {
+      load_cols(i0, pc, sc, wb);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -582,9 +598,39 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
   }
 }
 
+template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
+__global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  gemv_body<T, V, NT, MAIN_SMEM, RES>(p, smem, blockIdx.x, gridDim.x);
+}
+
+// Horizontal fusion: up to 4 layers that read the SAME x (q/k/v, gate/up) in ONE launch.  The grid is
+// the concatenation of the layers' own grids (each planned for its share of the SMs); a CTA finds
+// its layer from blockIdx.x and then runs the ordinary per-layer body.  One launch, one prologue
+// latency, no idle SMs behind a small layer.
+constexpr int kMaxFused = 4;
+struct GemvMultiParams {
+  int n;
+  uint32_t grid_begin[kMaxFused + 1];  // layer l owns blocks [grid_begin[l], grid_begin[l+1])
+  GemvParams layer[kMaxFused];
+};
+
+template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
+__global__ void __launch_bounds__(512, 1) gemv_multi_kernel(const __grid_constant__ GemvMultiParams mp) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  int l = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxFused; ++i)
+    if (i < mp.n && blockIdx.x >= mp.grid_begin[i]) l = i;
+  gemv_body<T, V, NT, MAIN_SMEM, RES>(mp.layer[l], smem, blockIdx.x - mp.grid_begin[l],
+                                     mp.grid_begin[l + 1] - mp.grid_begin[l]);
+}
+
 using GemvKernelFn = void (*)(const GemvParams);
+using GemvMultiKernelFn = void (*)(const GemvMultiParams);
 // one definition per (dtype, V) translation unit, see gemv_inst_*.cu
 GemvKernelFn gemv_kernel_v8(int dtype, int nt, bool main_smem, bool res);
 GemvKernelFn gemv_kernel_vx(int dtype, int v, bool main_smem, bool res);
+GemvMultiKernelFn gemv_multi_kernel_v8(int dtype, int nt, bool main_smem, bool res);
 
 }  // namespace vptq_b200

@@ -25,7 +25,7 @@ ABI_VERSION = 2
 EXPORTS = (
     "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
     "vptq_b200_dequant", "vptq_b200_quant_gemm", "vptq_b200_quant_gemv_v2", "vptq_b200_linear_host",
-    "vptq_b200_debug_phase_stamps",
+    "vptq_b200_debug_phase_stamps", "vptq_b200_quant_gemv_multi",
 )
 
 
@@ -77,6 +77,9 @@ def lib() -> ctypes.CDLL:
         L.vptq_b200_quant_gemv_v2.argtypes = [i32, vp, vp, i32, i32, i32, i32, i32, i32, vp, vp, vp, i32, vp, vp,
                                               vp, vp, vp, sz, u32, vp]
         L.vptq_b200_linear_host.argtypes = [dp, vp, vp, i32, vp, vp, vp, sz, u32, vp]
+        L.vptq_b200_quant_gemv_multi.argtypes = [i32, ctypes.POINTER(dp), vp, i64, ctypes.POINTER(vp),
+                                                 ctypes.POINTER(i64), i32, u32, vp]
+        L.vptq_b200_quant_gemv_multi.restype = ctypes.c_int
         L.vptq_b200_debug_phase_stamps.argtypes = [vp]
         L.vptq_b200_debug_phase_stamps.restype = None
         for f in ("vptq_b200_quant_gemv", "vptq_b200_quant_gemm", "vptq_b200_dequant", "vptq_b200_quant_gemv_v2",
@@ -203,6 +206,24 @@ def quant_gemv(desc: LinearDesc, x2d: torch.Tensor, y2d: torch.Tensor, flags: in
         rc = lib().vptq_b200_quant_gemv(ctypes.byref(desc), x2d.data_ptr(), x2d.stride(0), y2d.data_ptr(),
                                         y2d.stride(0), tokens, ws.data_ptr(), ws.numel(), flags, _stream(dev))
     check(rc, "vptq_b200_quant_gemv")
+
+
+class FusedGemv:
+    """Prepared argument arrays for vptq_b200_quant_gemv_multi (layers sharing one input)."""
+
+    def __init__(self, descs, ys):
+        n = len(descs)
+        self.n, self.descs, self.ys = n, list(descs), list(ys)
+        self.desc_arr = (ctypes.POINTER(LinearDesc) * n)(*[ctypes.pointer(d) for d in descs])
+        self.y_arr = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
+        self.stride_arr = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
+
+    def __call__(self, x2d: torch.Tensor, flags: int = 0) -> None:
+        dev = x2d.device
+        with torch.cuda.device(dev):
+            rc = lib().vptq_b200_quant_gemv_multi(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0), self.y_arr,
+                                                  self.stride_arr, x2d.shape[0], flags, _stream(dev))
+        check(rc, "vptq_b200_quant_gemv_multi")
 
 
 def quant_gemm(desc: LinearDesc, x2d: torch.Tensor, y2d: torch.Tensor, flags: int = 0) -> None:
