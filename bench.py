@@ -142,14 +142,20 @@ def make_step(m, stack, device, dtype, rank, world, flags):
     import torch.distributed as dist
     from vptq_b200 import native
     h, kv, f = m["hidden"], m["kv"], m["ffn"]
-    buf = {n: torch.zeros(1, o, device=device, dtype=dtype) for n, o in
-           (("q", h), ("k", kv), ("v", kv), ("o", h), ("gate", f), ("up", f))}
+    # q|k|v and gate|up live side by side so that one memset + one all-reduce serve a fused launch
+    qkv = torch.zeros(1, h + 2 * kv, device=device, dtype=dtype)
+    gu = torch.zeros(1, 2 * f, device=device, dtype=dtype)
+    buf = {"q": qkv[:, :h], "k": qkv[:, h:h + kv], "v": qkv[:, h + kv:], "gate": gu[:, :f], "up": gu[:, f:],
+           "o": torch.zeros(1, h, device=device, dtype=dtype)}
     # x_in is read-only (so that replaying the graph repeats the same token); hidden states ping-pong
     x_in = torch.zeros(1, h, device=device, dtype=dtype)
     hs = [torch.zeros(1, h, device=device, dtype=dtype) for _ in range(2)]
     launches = [0]
-
     debug_sync = bool(os.environ.get("BENCH_DEBUG"))
+
+    def own(t, y):
+        """this rank's slice of a full-width output"""
+        return y if world == 1 else y[:, rank * t["out_loc"]:(rank + 1) * t["out_loc"]]
 
     def linear(t, x, y):
         if world == 1:
@@ -160,26 +166,36 @@ def make_step(m, stack, device, dtype, rank, world, flags):
             # this rank owns rows [rank*o_loc, (rank+1)*o_loc); y is full width and zero elsewhere,
             # one all-reduce(sum) over NVLink per layer completes it (north_star)
             y.zero_()
-            ys = y[:, rank * t["out_loc"]:(rank + 1) * t["out_loc"]]
-            native.quant_gemv(t["desc"], x, ys, flags=0)
+            native.quant_gemv(t["desc"], x, own(t, y), flags=0)
             dist.all_reduce(y)
         launches[0] += 1
 
-    fuse = world == 1 and not os.environ.get("BENCH_NO_FUSE")
+    fuse = not os.environ.get("BENCH_NO_FUSE")
     fused = []
     if fuse:   # horizontal fusion of the linears that share an input: 7 -> 4 launches per layer
         for layer in stack:
-            fused.append((native.FusedGemv([layer[n]["desc"] for n in ("q", "k", "v")], [buf["q"], buf["k"], buf["v"]]),
-                          native.FusedGemv([layer[n]["desc"] for n in ("gate", "up")], [buf["gate"], buf["up"]])))
+            fused.append((native.FusedGemv([layer[n]["desc"] for n in ("q", "k", "v")],
+                                           [own(layer[n], buf[n]) for n in ("q", "k", "v")]),
+                          native.FusedGemv([layer[n]["desc"] for n in ("gate", "up")],
+                                           [own(layer[n], buf[n]) for n in ("gate", "up")])))
+
+    def fused_linear(fn, x, full):
+        if world == 1:
+            fn(x, flags)
+        else:   # one memset + one launch + ONE all-reduce for the whole group
+            full.zero_()
+            fn(x, 0)
+            dist.all_reduce(full)
+        launches[0] += 1
 
     def step():
         launches[0] = 0
         x, cur = x_in, 0
         for li, layer in enumerate(stack):
             if fuse:
-                fused[li][0](x, flags); launches[0] += 1
+                fused_linear(fused[li][0], x, qkv)
                 linear(layer["o"], buf["q"], buf["o"])
-                fused[li][1](buf["o"], flags); launches[0] += 1
+                fused_linear(fused[li][1], buf["o"], gu)
             else:
                 linear(layer["q"], x, buf["q"])
                 linear(layer["k"], x, buf["k"])
@@ -323,10 +339,10 @@ def run_ours(args):
             "config": {"workload": "BASELINE.json configs[1]: Llama-3-8B decode batch=1 seq=1, all 224 VPTQ linears "
                                    "(32 layers x q,k,v,o,gate,up,down), v=8 K=65536 Kr=256 (b=24), perm+norm on; "
                                    "attention/norm/lm_head not on the VPTQ path and not executed",
-                       "parallelism": f"tp{world} (out_features sharded, 1 NCCL all-reduce per linear)" if world > 1 else "single GPU",
+                       "parallelism": f"tp{world} (out_features sharded; 1 NCCL all-reduce per launch: q|k|v, o, gate|up, down)" if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2: 2.6 GB of distinct packed indices streamed per step",
                        "fusion": "q+k+v and gate+up each in one launch (vptq_b200_quant_gemv_multi)" if
-                                 (world == 1 and not os.environ.get("BENCH_NO_FUSE")) else "one launch per linear",
+                                 not os.environ.get("BENCH_NO_FUSE") else "one launch per linear",
                        "launch": ("one CUDA graph per token" if use_graph else "eager launches") +
                                  ", PDL " + ("off" if (args.no_pdl or world > 1) else "on")},
             "gpu_launches": n_launch * args.steps,

@@ -168,7 +168,8 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
   const T* wbias = reinterpret_cast<const T*>(p.wbias);
   const T* scale_q = reinterpret_cast<const T*>(p.scale_q);
   const T* wbias_q = reinterpret_cast<const T*>(p.wbias_q);
-  auto load_cols = [&](int i0, int (&pc)[4], float (&sc)[4], float (&wb)[4]) {
+  // loads only (raw 16-bit values, no conversions: nothing here waits for the data)
+  auto load_cols = [&](int i0, int (&pc)[4], T (&sc)[4], T (&wb)[4], bool early) {
     int cc[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -179,14 +180,15 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      // quantised-order copies (built once at load time) cut the perm -> scale dependent-load chain
-      sc[k] = scale_q ? DT<T>::to_float(scale_q[cc[k]]) : (scale ? DT<T>::to_float(scale[pc[k]]) : 1.f);
-      wb[k] = wbias_q ? DT<T>::to_float(wbias_q[cc[k]]) : (wbias ? DT<T>::to_float(wbias[pc[k]]) : 0.f);
+      // quantised-order copies (built once at load time) cut the perm -> scale dependent-load chain;
+      // without them the dependent gathers are left for phase A (`early` must not wait for perm)
+      if (scale_q) sc[k] = scale_q[cc[k]], wb[k] = wbias_q[cc[k]];
+      else if (!early) sc[k] = scale ? scale[pc[k]] : DT<T>::from_float(1.f), wb[k] = wbias ? wbias[pc[k]] : DT<T>::from_float(0.f);
     }
   };
   int pc0[4];
-  float sc0[4], wb0[4];
-  load_cols(tid, pc0, sc0, wb0);
+  T sc0[4], wb0[4];
+  load_cols(tid, pc0, sc0, wb0, true);
 
   // -------- barrier init -----------------------------------------------------------------
   {
@@ -305,17 +307,21 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
   }
   for (int i0 = tid; i0 < n_all; i0 += 4 * blockDim.x) {
     int pc[4];
-    float sc[4], wb[4];
+    T sc[4], wb[4];
     if (i0 == tid) {  // the batch whose loads were issued at kernel entry
 #pragma unroll
-      for (int k = 0; k < 4; ++k) pc[k] = pc0[k], sc[k] = sc0[k], wb[k] = wb0[k];
+      for (int k = 0; k < 4; ++k) {
+        pc[k] = pc0[k];
+        if (scale_q) sc[k] = sc0[k], wb[k] = wb0[k];
+        else sc[k] = scale ? scale[pc[k]] : DT<T>::from_float(1.f), wb[k] = wbias ? wbias[pc[k]] : DT<T>::from_float(0.f);
+      }
     } else {
-      load_cols(i0, pc, sc, wb);
+      load_cols(i0, pc, sc, wb, false);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int i = i0 + k * blockDim.x;
-      if (i < n_all) s_pcol[i] = uint16_t(pc[k]), sx[i] = sc[k], s_wb[i] = wb[k];
+      if (i < n_all) s_pcol[i] = uint16_t(pc[k]), sx[i] = DT<T>::to_float(sc[k]), s_wb[i] = DT<T>::to_float(wb[k]);
     }
   }
 
