@@ -16,7 +16,7 @@ namespace {
 
 constexpr int kMaxChunkCols = 4096;      // bounds the x' slice in shared memory (16 KB per token)
 constexpr int kSmemReserve = 2048;       // head-room below the opt-in limit
-constexpr int kMaxClusterPartBytes = 8192;
+constexpr int kMaxClusterPartBytes = 16384;
 
 bool supported_vec_len(int v) { return v == 2 || v == 4 || v == 6 || v == 8 || v == 10 || v == 12 || v == 16; }
 

@@ -217,13 +217,20 @@ class FusedGemv:
         self.desc_arr = (ctypes.POINTER(LinearDesc) * n)(*[ctypes.pointer(d) for d in descs])
         self.y_arr = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
         self.stride_arr = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
+        self.separate = False
 
     def __call__(self, x2d: torch.Tensor, flags: int = 0) -> None:
         dev = x2d.device
-        with torch.cuda.device(dev):
-            rc = lib().vptq_b200_quant_gemv_multi(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0), self.y_arr,
-                                                  self.stride_arr, x2d.shape[0], flags, _stream(dev))
-        check(rc, "vptq_b200_quant_gemv_multi")
+        if not self.separate:
+            with torch.cuda.device(dev):
+                rc = lib().vptq_b200_quant_gemv_multi(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0), self.y_arr,
+                                                      self.stride_arr, x2d.shape[0], flags, _stream(dev))
+            if rc != -2:                      # VPTQ_ERR_UNSUPPORTED: these layers cannot share one launch
+                check(rc, "vptq_b200_quant_gemv_multi")
+                return
+            self.separate = True              # same kernels, one launch per layer (identical results)
+        for d, y in zip(self.descs, self.ys):
+            quant_gemv(d, x2d, y, flags)
 
 
 def quant_gemm(desc: LinearDesc, x2d: torch.Tensor, y2d: torch.Tensor, flags: int = 0) -> None:
