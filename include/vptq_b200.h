@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define VPTQ_B200_ABI_VERSION 2
+#define VPTQ_B200_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define VPTQ_B200_API __attribute__((visibility("default")))
@@ -157,6 +157,35 @@ VPTQ_B200_API int vptq_b200_quant_gemv(const vptq_linear_desc* desc, const void*
 VPTQ_B200_API int vptq_b200_quant_gemv_multi(int32_t n, const vptq_linear_desc* const* descs, const void* x,
                                              int64_t x_stride, void* const* ys, const int64_t* y_strides,
                                              int32_t tokens, uint32_t flags, void* stream);
+
+/*
+ * Tensor-parallel decode with the exchange fused into the kernel (no NCCL call, no memset):
+ * every rank passes pointers to the SAME y slice inside every rank's full-width output buffer
+ * (peer-mapped device memory: CUDA IPC / symmetric memory, peer access enabled by the caller).
+ * The kernel stores each output value locally and into all peers over NVLink; the last CTA
+ * publishes this launch's epoch in every peer's flag array; a launch with wait_slot >= 0 polls
+ * the flags of the launch that produced its x before reading it.  All ranks must issue the same
+ * sequence of launches; `slot` identifies a launch position within one token (static under CUDA
+ * graphs: the epochs live in device memory).  No reference counterpart.
+ */
+#define VPTQ_MAX_FUSED 4
+#define VPTQ_MAX_RANKS 8
+typedef struct vptq_tp_exchange {
+  uint32_t struct_size;
+  int32_t world, rank;
+  int32_t slot;      /* this launch's position in the token, 0 <= slot < num_slots */
+  int32_t wait_slot; /* launch whose outputs are this launch's x; -1: x is local (replicated) */
+  void* peer_y[VPTQ_MAX_FUSED][VPTQ_MAX_RANKS]; /* [layer][rank]: start of THIS rank's slice in rank r's y */
+  uint32_t* peer_flags[VPTQ_MAX_RANKS];         /* rank r's flag array, uint32 [num_slots][world] */
+  uint32_t* epoch;   /* local uint32 [num_slots], zero-initialised once */
+  uint32_t* done;    /* local uint32 [num_slots], zero-initialised once */
+  uint32_t* error;   /* local uint32, set to 1 when a flag wait timed out (~2 s) */
+} vptq_tp_exchange;
+
+VPTQ_B200_API int vptq_b200_quant_gemv_multi_tp(int32_t n, const vptq_linear_desc* const* descs, const void* x,
+                                                int64_t x_stride, void* const* ys, const int64_t* y_strides,
+                                                int32_t tokens, const vptq_tp_exchange* tp, uint32_t flags,
+                                                void* stream);
 
 /*
  * W[o][f] (row-major [O][I], `dtype`), scale/bias/perm applied -- what the reference's dequant

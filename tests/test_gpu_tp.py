@@ -63,3 +63,77 @@ def test_tp_two_gpus_nccl():
         assert p.exitcode == 0
     for rank, err in res:
         assert err <= 1e-3, (rank, err)
+
+
+def _worker_p2p(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        import sys
+        here = os.path.dirname(os.path.abspath(__file__))
+        for p in (os.path.dirname(here), os.path.join(os.path.dirname(here), "oracle"), here):
+            sys.path.insert(0, p)
+        import vptq_oracle as vo
+        from _gpu import make_module, x_to_t
+        from vptq_b200 import native, tp
+        # two chained layers: A (1024 -> 2048) then B (2048 -> 1024); x of B = exchanged output of A
+        LA = vo.make_layer(in_features=1024, out_features=2048, vector_len=8, num_centroids=65536, num_res_centroids=256, seed=41)
+        LB = vo.make_layer(in_features=2048, out_features=1024, vector_len=8, num_centroids=4096, num_res_centroids=256, seed=42)
+        shards = []
+        for L in (LA, LB):
+            full = make_module(L, f"cuda:{rank}")
+            sh = tp.shard_module(full, rank, world).shard
+            sh(torch.zeros(0, L.in_features, device=dev, dtype=torch.float16))     # builds the descriptor
+            shards.append(sh)
+        arena = tp.PeerArena(1 << 20, dev)
+        yA, offA = arena.alloc((1, 2048), torch.float16)
+        yB, offB = arena.alloc((1, 1024), torch.float16)
+        flags, off_flags = arena.alloc((2, world), torch.int32)
+        epoch = torch.zeros(2, dtype=torch.int32, device=dev)
+        done = torch.zeros(2, dtype=torch.int32, device=dev)
+        error = torch.zeros(1, dtype=torch.int32, device=dev)
+        locA, locB = 2048 // world, 1024 // world
+        exA = tp.make_exchange(arena, slot=0, wait_slot=-1, y_offsets=[offA], slice_bytes=[rank * locA * 2],
+                               flags_offset=off_flags, epoch=epoch, done=done, error=error)
+        exB = tp.make_exchange(arena, slot=1, wait_slot=0, y_offsets=[offB], slice_bytes=[rank * locB * 2],
+                               flags_offset=off_flags, epoch=epoch, done=done, error=error)
+        fA = native.FusedGemvTP([shards[0]._desc_cache[0]], [yA[:, rank * locA:(rank + 1) * locA]], exA)
+        fB = native.FusedGemvTP([shards[1]._desc_cache[0]], [yB[:, rank * locB:(rank + 1) * locB]], exB)
+        errs = []
+        for it in range(4):                      # repeated tokens: epochs advance, buffers are reused
+            x_np = vo.make_x(1, 1024, "fp16", seed=100 + it)
+            x = x_to_t(x_np, LA, f"cuda:{rank}")
+            fA(x)
+            fB(yA)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a_star = vo.quant_gemm(x_np, LA)
+            b_star = vo.quant_gemm(a_star.astype(np.float16), LB)
+            errs.append(float(np.abs(yA.float().cpu().numpy() - a_star).max() / np.abs(a_star).max()))
+            errs.append(float(np.abs(yB.float().cpu().numpy() - b_star).max() / np.abs(b_star).max()))
+        q.put((rank, max(errs), int(error.item())))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tp_fused_p2p_exchange_two_gpus():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_p2p, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, flag in res:
+        assert flag == 0, "a flag wait timed out"
+        assert err <= 2e-3, (rank, err)      # layer B sees fp16-rounded activations of layer A

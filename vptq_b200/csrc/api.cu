@@ -204,6 +204,38 @@ int vptq_b200_quant_gemv_multi(int32_t n, const vptq_linear_desc* const* descs, 
   return gemv_multi_launch(n, descs, x, x_stride, ys, y_strides, tokens, flags, static_cast<cudaStream_t>(stream));
 }
 
+int vptq_b200_quant_gemv_multi_tp(int32_t n, const vptq_linear_desc* const* descs, const void* x, int64_t x_stride,
+                                  void* const* ys, const int64_t* y_strides, int32_t tokens,
+                                  const vptq_tp_exchange* tp, uint32_t flags, void* stream) {
+  if (!descs || !x || !ys || !y_strides || n < 1 || !tp) {
+    set_error("quant_gemv_multi_tp: NULL argument");
+    return VPTQ_ERR_INVALID;
+  }
+  if (tp->struct_size != sizeof(vptq_tp_exchange) || tp->world < 1 || tp->world > VPTQ_MAX_RANKS || tp->rank < 0 ||
+      tp->rank >= tp->world || tp->slot < 0 || !tp->epoch || !tp->done || !tp->error) {
+    set_error("quant_gemv_multi_tp: bad vptq_tp_exchange (size %u, world %d, rank %d, slot %d)", tp->struct_size,
+              tp->world, tp->rank, tp->slot);
+    return VPTQ_ERR_INVALID;
+  }
+  for (int l = 0; l < n; ++l) {
+    if (int rc = validate(descs[l], l == 0)) return rc;
+    if (!ys[l] || y_strides[l] < descs[l]->out_features || x_stride < descs[l]->in_features) {
+      set_error("quant_gemv_multi_tp: bad y / stride for layer %d", l);
+      return VPTQ_ERR_INVALID;
+    }
+    for (int r = 0; r < tp->world; ++r)
+      if (r != tp->rank && (!tp->peer_y[l][r] || !tp->peer_flags[r])) {
+        set_error("quant_gemv_multi_tp: NULL peer pointer (layer %d, rank %d)", l, r);
+        return VPTQ_ERR_INVALID;
+      }
+  }
+  if (flags & VPTQ_FLAG_PDL) {
+    set_error("quant_gemv_multi_tp: programmatic dependent launch is not supported together with flag waits");
+    return VPTQ_ERR_UNSUPPORTED;
+  }
+  return gemv_multi_launch(n, descs, x, x_stride, ys, y_strides, tokens, flags, static_cast<cudaStream_t>(stream), tp);
+}
+
 int vptq_b200_dequant(const vptq_linear_desc* desc, void* w_out, void* workspace, size_t workspace_bytes,
                       void* stream) {
   if (int rc = validate(desc, true)) return rc;

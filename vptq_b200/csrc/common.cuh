@@ -142,6 +142,20 @@ __device__ __forceinline__ uint32_t ldg_nc_u32(const void* p) {
   asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(r) : "l"(p));
   return r;
 }
+// system-scope flag traffic between GPUs (tensor-parallel epoch flags in peer memory)
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t r;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+  uint32_t r;
+  asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(r) : "l"(p) : "memory");
+  return r;
+}
 // L2-coherent load (bypasses L1): used to read partial sums written by other SMs
 __device__ __forceinline__ float ldg_cg_f32(const float* p) {
   float r;

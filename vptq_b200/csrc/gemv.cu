@@ -388,7 +388,8 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
 // instantiation, one block size and one cluster size for all of them -- otherwise (or when a layer
 // needs the global-memory split-K variant) VPTQ_ERR_UNSUPPORTED tells the caller to launch separately.
 int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x, int64_t x_stride, void* const* ys,
-                      const int64_t* y_strides, int tokens, uint32_t flags, cudaStream_t stream) {
+                      const int64_t* y_strides, int tokens, uint32_t flags, cudaStream_t stream,
+                      const vptq_tp_exchange* tp) {
   const DeviceInfo* dev = device_info();
   if (!dev) return VPTQ_ERR_CUDA;
   if (n < 1 || n > kMaxFused || tokens < 1 || tokens > 2) {
@@ -452,6 +453,12 @@ int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x
     fill_params(mp.layer[l], *descs[l], pl, x_stride, y_strides[l], nullptr);
     mp.layer[l].x = x;
     mp.layer[l].y = ys[l];
+    if (tp && tp->world > 1) {
+      GemvParams& q = mp.layer[l];
+      q.tp_world = tp->world, q.tp_rank = tp->rank, q.tp_slot = tp->slot, q.tp_wait_slot = tp->wait_slot;
+      for (int r = 0; r < tp->world; ++r) q.tp_peer_y[r] = tp->peer_y[l][r], q.tp_peer_flags[r] = tp->peer_flags[r];
+      q.tp_epoch = tp->epoch, q.tp_done = tp->done, q.tp_error = tp->error;
+    }
     mp.grid_begin[l] = begin;
     begin += uint32_t(pl.grid);
     smem = std::max(smem, pl.smem_bytes);

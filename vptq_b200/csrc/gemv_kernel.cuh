@@ -57,6 +57,16 @@ struct GemvParams {
   int I, O, Ro, G, gs, S, vol, Kol, Rol;
   int K, Kr, ib, rb;
   int idx_tma_ok;  // rows are 16-byte aligned -> bulk copies legal
+  // tensor-parallel exchange over peer memory (tp_world <= 1: off).  The kernel stores every output
+  // value into the same slot of every rank's full-width y (NVLink stores), the last CTA to finish
+  // publishes a per-launch epoch flag on every peer, and the consumer launch polls those flags
+  // before it reads x: no memset, no NCCL call, no extra kernel between two layers.
+  int tp_world, tp_rank, tp_slot, tp_wait_slot;
+  void* tp_peer_y[8];             // y slice start in rank r's buffer (entry [tp_rank] unused)
+  uint32_t* tp_peer_flags[8];     // rank r's flag array [slots][world]; [tp_rank] = the local one
+  uint32_t* tp_epoch;             // local: completed runs per launch slot
+  uint32_t* tp_done;              // local: CTA arrival counters per launch slot (zero at rest)
+  uint32_t* tp_error;             // local: set when a flag wait timed out
   unsigned long long* prof;  // developer aid: per-phase %globaltimer stamps of CTA 0 / last CTA (or nullptr)
   GemvPlan plan;
 };
@@ -116,7 +126,8 @@ __device__ __forceinline__ float warp_reduce_to_lane(float (&acc)[V], int lane) 
 // One CTA's share of one layer.  `bidx` / `gdim`: this CTA's index within, and the size of, the
 // layer's own grid (a fused launch concatenates the grids of several layers, see gemv_multi_kernel).
 template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
-__device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, const uint32_t bidx, const uint32_t gdim) {
+__device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, const uint32_t bidx, const uint32_t gdim,
+                                          const uint32_t gdim_total) {
   constexpr int U = (NT == 1 && V <= 8) ? 8 : 4;  // independent codebook gathers in flight per lane
   constexpr int EB = 2 * V;                       // bytes per codebook entry
   const GemvPlan& pl = p.plan;
@@ -344,6 +355,26 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
   stamp(4);
   // -------- phase B: x arrives from the previous kernel ------------------------------------
   pdl_wait_prior_grid();
+  if (p.tp_world > 1 && p.tp_wait_slot >= 0) {
+    // x is assembled from every rank's slice: wait until all peers have published the epoch of the
+    // launch that produces it (this launch's own run number: both run once per token)
+    if (tid == 0) {
+      const uint32_t want = ld_volatile_u32(p.tp_epoch + p.tp_slot) + 1u;
+      const uint32_t* mine = p.tp_peer_flags[p.tp_rank] + p.tp_wait_slot * p.tp_world;
+      const long long t0 = clock64();
+      for (int r = 0; r < p.tp_world; ++r) {
+        if (r == p.tp_rank) continue;
+        while (ld_acquire_sys_u32(mine + r) < want) {
+          if (clock64() - t0 > (1ll << 32)) {  // ~2 s: give up loudly instead of hanging the GPU
+            *p.tp_error = 1u;
+            break;
+          }
+        }
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+  }
   stamp(5);
   {
     const T* x = reinterpret_cast<const T*>(p.x);
@@ -403,6 +434,18 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
   const uint32_t bar_leader = pl.cluster ? mapa_shared(smem_u32(part_bar), 0) : 0u;
   const T* bias = reinterpret_cast<const T*>(p.bias);
   T* y = reinterpret_cast<T*>(p.y);
+
+  // the one place y is written: locally and, under tensor parallelism, into every peer's buffer
+  auto store_y = [&](int t, int o, float v) {
+    const T hv = DT<T>::from_float(v);
+    const int64_t off = int64_t(t) * p.y_stride + o;
+    y[off] = hv;
+    if (p.tp_world > 1) {
+#pragma unroll 1
+      for (int r = 0; r < p.tp_world; ++r)
+        if (r != p.tp_rank) reinterpret_cast<T*>(p.tp_peer_y[r])[off] = hv;
+    }
+  };
 
   float acc[NT][V];
 #pragma unroll
@@ -480,7 +523,7 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
       if (writer) {
         const float bv = bias ? DT<T>::to_float(bias[o]) : 0.f;
 #pragma unroll
-        for (int t = 0; t < NT; ++t) y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(mine[t] + bv);
+        for (int t = 0; t < NT; ++t) store_y(t, o, mine[t] + bv);
       }
     } else if (pl.cluster) {
       // DSMEM hand-off: slot [krow][chunk][t][e] of the leader's (rank 0) partial-sum table
@@ -509,7 +552,7 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
           for (int t = 0; t < NT; ++t) {
             float v = 0.f;
             for (int ch = 0; ch < pl.nch; ++ch) v += ldg_cg_f32(&p.partials[(int64_t(ch) * NT + t) * opad + r * V + lane]);
-            y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(v + bv);
+            store_y(t, o, v + bv);
           }
         }
         if (lane == 0) p.counters[r] = 0u;  // leave the counter region zeroed for the next launch
@@ -598,7 +641,7 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
       if (o < p.O) {
         float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
         for (int ch = 0; ch < pl.nch; ++ch) v += s_part[((krow * pl.nch + ch) * NT + t) * V + e];
-        y[int64_t(t) * p.y_stride + o] = DT<T>::from_float(v);
+        store_y(t, o, v);
       }
     }
   }
@@ -607,7 +650,7 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
 template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
 __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ GemvParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  gemv_body<T, V, NT, MAIN_SMEM, RES>(p, smem, blockIdx.x, gridDim.x);
+  gemv_body<T, V, NT, MAIN_SMEM, RES>(p, smem, blockIdx.x, gridDim.x, gridDim.x);
 }
 
 // Horizontal fusion: up to 4 layers that read the SAME x (q/k/v, gate/up) in ONE launch.  The grid is
@@ -629,7 +672,7 @@ __global__ void __launch_bounds__(512, 1) gemv_multi_kernel(const __grid_constan
   for (int i = 1; i < kMaxFused; ++i)
     if (i < mp.n && blockIdx.x >= mp.grid_begin[i]) l = i;
   gemv_body<T, V, NT, MAIN_SMEM, RES>(mp.layer[l], smem, blockIdx.x - mp.grid_begin[l],
-                                     mp.grid_begin[l + 1] - mp.grid_begin[l]);
+                                     mp.grid_begin[l + 1] - mp.grid_begin[l], gridDim.x);
 }
 
 using GemvKernelFn = void (*)(const GemvParams);

@@ -73,7 +73,8 @@ struct GemvPlan {
 int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev, GemvPlan* plan, int slots_override = 0,
                    int force_cpg = 0);
 int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x, int64_t x_stride, void* const* ys,
-                      const int64_t* y_strides, int tokens, uint32_t flags, cudaStream_t stream);
+                      const int64_t* y_strides, int tokens, uint32_t flags, cudaStream_t stream,
+                      const vptq_tp_exchange* tp = nullptr);
 void gemv_set_profile_buffer(void* dev_ptr);
 // Launches ceil(tokens / plan.nt) passes.
 int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void* y, int64_t y_stride,

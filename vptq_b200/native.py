@@ -20,13 +20,25 @@ LIB_PATH = os.path.join(_HERE, "libvptq_b200.so")
 VPTQ_FP16, VPTQ_BF16 = 0, 1
 OP_GEMV, OP_DEQUANT, OP_GEMM, OP_GEMV_V2 = 0, 1, 2, 3
 FLAG_PDL = 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 EXPORTS = (
     "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
     "vptq_b200_dequant", "vptq_b200_quant_gemm", "vptq_b200_quant_gemv_v2", "vptq_b200_linear_host",
-    "vptq_b200_debug_phase_stamps", "vptq_b200_quant_gemv_multi",
+    "vptq_b200_debug_phase_stamps", "vptq_b200_quant_gemv_multi", "vptq_b200_quant_gemv_multi_tp",
 )
+
+MAX_FUSED, MAX_RANKS = 4, 8
+
+
+class TpExchange(ctypes.Structure):
+    """struct vptq_tp_exchange (include/vptq_b200.h)."""
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32), ("world", ctypes.c_int32), ("rank", ctypes.c_int32),
+        ("slot", ctypes.c_int32), ("wait_slot", ctypes.c_int32),
+        ("peer_y", (ctypes.c_void_p * MAX_RANKS) * MAX_FUSED), ("peer_flags", ctypes.c_void_p * MAX_RANKS),
+        ("epoch", ctypes.c_void_p), ("done", ctypes.c_void_p), ("error", ctypes.c_void_p),
+    ]
 
 
 class LinearDesc(ctypes.Structure):
@@ -80,6 +92,9 @@ def lib() -> ctypes.CDLL:
         L.vptq_b200_quant_gemv_multi.argtypes = [i32, ctypes.POINTER(dp), vp, i64, ctypes.POINTER(vp),
                                                  ctypes.POINTER(i64), i32, u32, vp]
         L.vptq_b200_quant_gemv_multi.restype = ctypes.c_int
+        L.vptq_b200_quant_gemv_multi_tp.argtypes = [i32, ctypes.POINTER(dp), vp, i64, ctypes.POINTER(vp),
+                                                    ctypes.POINTER(i64), i32, ctypes.POINTER(TpExchange), u32, vp]
+        L.vptq_b200_quant_gemv_multi_tp.restype = ctypes.c_int
         L.vptq_b200_debug_phase_stamps.argtypes = [vp]
         L.vptq_b200_debug_phase_stamps.restype = None
         for f in ("vptq_b200_quant_gemv", "vptq_b200_quant_gemm", "vptq_b200_dequant", "vptq_b200_quant_gemv_v2",
@@ -231,6 +246,24 @@ class FusedGemv:
             self.separate = True              # same kernels, one launch per layer (identical results)
         for d, y in zip(self.descs, self.ys):
             quant_gemv(d, x2d, y, flags)
+
+
+class FusedGemvTP:
+    """vptq_b200_quant_gemv_multi_tp: fused layers + the tensor-parallel exchange inside the kernel."""
+
+    def __init__(self, descs, ys, exchange: TpExchange):
+        n = len(descs)
+        self.n, self.descs, self.ys, self.ex = n, list(descs), list(ys), exchange
+        self.desc_arr = (ctypes.POINTER(LinearDesc) * n)(*[ctypes.pointer(d) for d in descs])
+        self.y_arr = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
+        self.stride_arr = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
+
+    def __call__(self, x2d: torch.Tensor) -> None:
+        dev = x2d.device
+        with torch.cuda.device(dev):
+            rc = lib().vptq_b200_quant_gemv_multi_tp(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0), self.y_arr,
+                                                     self.stride_arr, x2d.shape[0], ctypes.byref(self.ex), 0, _stream(dev))
+        check(rc, "vptq_b200_quant_gemv_multi_tp")
 
 
 def quant_gemm(desc: LinearDesc, x2d: torch.Tensor, y2d: torch.Tensor, flags: int = 0) -> None:

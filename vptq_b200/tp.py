@@ -138,3 +138,61 @@ def shard_module(m: VQuantLinear, rank: int, world: int, group=None, mode: str =
         if m.enable_norm:
             s.weight_scale.data, s.weight_bias.data = m.weight_scale.data, m.weight_bias.data
     return TPVQuantLinear(s.eval(), m.out_features, rank, world, group, mode)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Exchange fused into the GEMV kernel: peer-mapped activation buffers + epoch flags (no NCCL call)
+# ---------------------------------------------------------------------------------------------------
+class PeerArena:
+    """One symmetric byte arena per rank, mapped into every rank of the group (NVLink peer access).
+
+    Sub-allocations are taken at identical offsets on every rank, so `peer_ptr(r, off)` is the address of
+    the same object in rank r's arena.  Built on torch.distributed._symmetric_memory (CUDA VMM handles
+    exchanged through the process group's store); nothing here is on the hot path.
+    """
+
+    def __init__(self, nbytes: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.nbytes = (int(nbytes) + 1023) // 1024 * 1024
+        self.buf = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=device)
+        self.handle = symm_mem.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+        self._top = 0
+
+    def alloc(self, shape, dtype) -> "tuple[torch.Tensor, int]":
+        """(local tensor view, byte offset) -- call in the same order with the same sizes on every rank."""
+        n = 1
+        for s in shape:
+            n *= int(s)
+        nb = n * torch.empty(0, dtype=dtype).element_size()
+        off = (self._top + 255) // 256 * 256
+        if off + nb > self.nbytes:
+            raise RuntimeError("PeerArena exhausted")
+        self._top = off + nb
+        return self.buf[off:off + nb].view(dtype).view(*shape), off
+
+    def peer_ptr(self, rank: int, offset: int) -> int:
+        return self.ptrs[rank] + offset
+
+
+def make_exchange(arena: PeerArena, *, slot: int, wait_slot: int, y_offsets, slice_bytes, flags_offset: int,
+                  epoch: torch.Tensor, done: torch.Tensor, error: torch.Tensor):
+    """Fill a vptq_tp_exchange for one launch: y_offsets[l] = byte offset (in the arena) of layer l's FULL-width
+    output buffer, slice_bytes[l] = byte offset of this rank's slice inside it."""
+    from . import native
+    ex = native.TpExchange()
+    import ctypes
+    ex.struct_size = ctypes.sizeof(native.TpExchange)
+    ex.world, ex.rank, ex.slot, ex.wait_slot = arena.world, arena.rank, slot, wait_slot
+    for l, (yo, sb) in enumerate(zip(y_offsets, slice_bytes)):
+        for r in range(arena.world):
+            ex.peer_y[l][r] = arena.peer_ptr(r, yo + sb)
+    for r in range(arena.world):
+        ex.peer_flags[r] = arena.peer_ptr(r, flags_offset)
+    ex.epoch, ex.done, ex.error = epoch.data_ptr(), done.data_ptr(), error.data_ptr()
+    return ex
