@@ -645,6 +645,24 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
       }
     }
   }
+
+  // -------- tensor-parallel hand-off: publish this launch's epoch on every peer ------------------
+  if (p.tp_world > 1) {
+    __threadfence_system();  // this thread's peer stores are visible system-wide
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t prev = atomicAdd(p.tp_done + p.tp_slot, 1u);
+      if (prev == gdim_total - 1u) {  // the whole launch (all fused layers) has stored its outputs
+        p.tp_done[p.tp_slot] = 0u;
+        const uint32_t e = ld_volatile_u32(p.tp_epoch + p.tp_slot) + 1u;
+        p.tp_epoch[p.tp_slot] = e;
+        __threadfence_system();
+        for (int r = 0; r < p.tp_world; ++r)
+          if (r != p.tp_rank) st_release_sys_u32(p.tp_peer_flags[r] + p.tp_slot * p.tp_world + p.tp_rank, e);
+      }
+    }
+  }
+  stamp(10);
 }
 
 template <typename T, int V, int NT, bool MAIN_SMEM, bool RES>
