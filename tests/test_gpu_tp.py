@@ -112,10 +112,11 @@ def _worker_p2p(rank, world, port, q):
             dist.barrier()
             torch.cuda.synchronize()
             a_star = vo.quant_gemm(x_np, LA)
-            b_star = vo.quant_gemm(a_star.astype(np.float16), LB)
-            errs.append(float(np.abs(yA.float().cpu().numpy() - a_star).max() / np.abs(a_star).max()))
+            a_got = yA.cpu().numpy()                                     # what layer B actually consumed
+            b_star = vo.quant_gemm(a_got, LB)
+            errs.append(float(np.abs(a_got.astype(np.float32) - a_star).max() / np.abs(a_star).max()))
             errs.append(float(np.abs(yB.float().cpu().numpy() - b_star).max() / np.abs(b_star).max()))
-        q.put((rank, max(errs), int(error.item())))
+        q.put((rank, errs, int(error.item())))
     finally:
         dist.destroy_process_group()
 
@@ -134,6 +135,6 @@ def test_tp_fused_p2p_exchange_two_gpus():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for rank, err, flag in res:
+    for rank, errs, flag in res:
         assert flag == 0, "a flag wait timed out"
-        assert err <= 2e-3, (rank, err)      # layer B sees fp16-rounded activations of layer A
+        assert max(errs) <= 1e-3, (rank, [f"{e:.2e}" for e in errs])
