@@ -136,20 +136,38 @@ def build_stack(m, q, device, rank, world, dtype):
     return stack
 
 
-def make_step(m, stack, device, dtype, rank, world, flags):
-    """Returns (x_in, h_out, fn) where fn() enqueues one decode token on the current stream."""
+def make_step(m, stack, device, dtype, rank, world, flags, tp_mode="nccl"):
+    """Returns (x_in, step, launches); step() enqueues one decode token on the current stream."""
     import torch
     import torch.distributed as dist
     from vptq_b200 import native
     h, kv, f = m["hidden"], m["kv"], m["ffn"]
-    # q|k|v and gate|up live side by side so that one memset + one all-reduce serve a fused launch
-    qkv = torch.zeros(1, h + 2 * kv, device=device, dtype=dtype)
-    gu = torch.zeros(1, 2 * f, device=device, dtype=dtype)
-    buf = {"q": qkv[:, :h], "k": qkv[:, h:h + kv], "v": qkv[:, h + kv:], "gate": gu[:, :f], "up": gu[:, f:],
-           "o": torch.zeros(1, h, device=device, dtype=dtype)}
+    p2p = world > 1 and tp_mode == "p2p"
+    if p2p:
+        # activations live in a symmetric arena mapped into every rank: the GEMV stores its slice into
+        # all peers' buffers and publishes an epoch flag; consumers poll the flags (no NCCL on the path)
+        from vptq_b200 import tp
+        nslots = 4 * len(stack)
+        arena = tp.PeerArena((h + 2 * kv + h + 2 * f + 2 * h) * 2 + nslots * world * 4 + 8192, device)
+        qkv, off_qkv = arena.alloc((1, h + 2 * kv), dtype)
+        o_buf, off_o = arena.alloc((1, h), dtype)
+        gu, off_gu = arena.alloc((1, 2 * f), dtype)
+        hs0, off_h0 = arena.alloc((1, h), dtype)
+        hs1, off_h1 = arena.alloc((1, h), dtype)
+        _, off_flags = arena.alloc((nslots, world), torch.int32)
+        tp_epoch = torch.zeros(nslots, dtype=torch.int32, device=device)
+        tp_done = torch.zeros(nslots, dtype=torch.int32, device=device)
+        tp_error = torch.zeros(1, dtype=torch.int32, device=device)
+    else:
+        # q|k|v and gate|up live side by side so that one memset + one all-reduce serve a fused launch
+        qkv = torch.zeros(1, h + 2 * kv, device=device, dtype=dtype)
+        gu = torch.zeros(1, 2 * f, device=device, dtype=dtype)
+        o_buf = torch.zeros(1, h, device=device, dtype=dtype)
+        hs0, hs1 = (torch.zeros(1, h, device=device, dtype=dtype) for _ in range(2))
+    buf = {"q": qkv[:, :h], "k": qkv[:, h:h + kv], "v": qkv[:, h + kv:], "gate": gu[:, :f], "up": gu[:, f:], "o": o_buf}
     # x_in is read-only (so that replaying the graph repeats the same token); hidden states ping-pong
     x_in = torch.zeros(1, h, device=device, dtype=dtype)
-    hs = [torch.zeros(1, h, device=device, dtype=dtype) for _ in range(2)]
+    hs = [hs0, hs1]
     launches = [0]
     debug_sync = bool(os.environ.get("BENCH_DEBUG"))
 
@@ -172,7 +190,7 @@ def make_step(m, stack, device, dtype, rank, world, flags):
 
     fuse = not os.environ.get("BENCH_NO_FUSE")
     fused = []
-    if fuse:   # horizontal fusion of the linears that share an input: 7 -> 4 launches per layer
+    if fuse and not p2p:   # horizontal fusion of the linears that share an input: 7 -> 4 launches per layer
         for layer in stack:
             fused.append((native.FusedGemv([layer[n]["desc"] for n in ("q", "k", "v")],
                                            [own(layer[n], buf[n]) for n in ("q", "k", "v")]),
@@ -188,9 +206,42 @@ def make_step(m, stack, device, dtype, rank, world, flags):
             dist.all_reduce(full)
         launches[0] += 1
 
+    p2p_launch = []
+    if p2p:
+        e2 = 2  # bytes per element
+        hs_off = [off_h0, off_h1]
+        for li, layer in enumerate(stack):
+            cur = li % 2
+
+            def ex(slot_in_layer, wait, y_offsets, names, layer=layer, li=li):
+                return tp.make_exchange(arena, slot=4 * li + slot_in_layer, wait_slot=wait, y_offsets=y_offsets,
+                                        slice_bytes=[rank * layer[n]["out_loc"] * e2 for n in names],
+                                        flags_offset=off_flags, epoch=tp_epoch, done=tp_done, error=tp_error)
+
+            def fz(names, ys_full, exch, layer=layer):
+                return native.FusedGemvTP([layer[n]["desc"] for n in names],
+                                          [own(layer[n], y) for n, y in zip(names, ys_full)], exch)
+
+            wait_x = -1 if li == 0 else 4 * (li - 1) + 3
+            p2p_launch.append((
+                fz(("q", "k", "v"), (buf["q"], buf["k"], buf["v"]),
+                   ex(0, wait_x, [off_qkv, off_qkv + h * e2, off_qkv + (h + kv) * e2], ("q", "k", "v"))),
+                fz(("o",), (buf["o"],), ex(1, 4 * li, [off_o], ("o",))),
+                fz(("gate", "up"), (buf["gate"], buf["up"]), ex(2, 4 * li + 1, [off_gu, off_gu + f * e2], ("gate", "up"))),
+                fz(("down",), (hs[cur],), ex(3, 4 * li + 2, [hs_off[cur]], ("down",)))))
+
     def step():
         launches[0] = 0
         x, cur = x_in, 0
+        if p2p:
+            for f_qkv, f_o, f_gu, f_down in p2p_launch:
+                f_qkv(x)
+                f_o(buf["q"])
+                f_gu(buf["o"])
+                f_down(buf["gate"])
+                launches[0] += 4
+                x, cur = hs[cur], 1 - cur
+            return x
         for li, layer in enumerate(stack):
             if fuse:
                 fused_linear(fused[li][0], x, qkv)
@@ -207,6 +258,7 @@ def make_step(m, stack, device, dtype, rank, world, flags):
             x, cur = hs[cur], 1 - cur
         return x
 
+    step.tp_error = tp_error if p2p else None
     return x_in, step, launches
 
 
@@ -242,7 +294,8 @@ def run_ours(args):
 
     stack = build_stack(m, q, device, rank, world, dtype)
     _log("weights built")
-    x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags)
+    tp_mode = args.tp_mode if world > 1 else "none"
+    x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags, tp_mode)
     x_host = torch.randn(1, m["hidden"]).to(dtype).pin_memory()
     y_host = torch.empty(1, m["hidden"], dtype=dtype).pin_memory()
 
@@ -291,6 +344,8 @@ def run_ours(args):
         ms = ev[0].elapsed_time(ev[1])
         clk = clocks.stop() if rank == 0 else None
         assert torch.isfinite(h_out.float()).all(), "activations overflowed"
+        if step.tp_error is not None:
+            assert int(step.tp_error.item()) == 0, "a tensor-parallel flag wait timed out"
 
         # ---- `e2e`: host buffers, H2D + D2H inside the timed region, per-step sync ------------------
         e2e_steps = args.steps
@@ -339,7 +394,10 @@ def run_ours(args):
             "config": {"workload": "BASELINE.json configs[1]: Llama-3-8B decode batch=1 seq=1, all 224 VPTQ linears "
                                    "(32 layers x q,k,v,o,gate,up,down), v=8 K=65536 Kr=256 (b=24), perm+norm on; "
                                    "attention/norm/lm_head not on the VPTQ path and not executed",
-                       "parallelism": f"tp{world} (out_features sharded; 1 NCCL all-reduce per launch: q|k|v, o, gate|up, down)" if world > 1 else "single GPU",
+                       "parallelism": (f"tp{world} (out_features sharded; " +
+                                       ("exchange fused into the GEMV: NVLink peer stores + epoch flags, no NCCL call"
+                                        if tp_mode == "p2p" else "1 NCCL all-reduce per launch: q|k|v, o, gate|up, down") + ")")
+                                      if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2: 2.6 GB of distinct packed indices streamed per step",
                        "fusion": "q+k+v and gate+up each in one launch (vptq_b200_quant_gemv_multi)" if
                                  not os.environ.get("BENCH_NO_FUSE") else "one launch per linear",
@@ -433,6 +491,8 @@ def main():
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--tp-mode", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: exchange fused into the GEMV over peer memory (p2p) or memset + NCCL all-reduce (nccl)")
     ap.add_argument("--tp-eager", action="store_true", help="N > 1: launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--debug-layers", type=int, default=0, help="debugging only: truncate the model (invalid as a result)")
     args = ap.parse_args()
