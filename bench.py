@@ -235,10 +235,10 @@ def make_step(m, stack, device, dtype, rank, world, flags, tp_mode="nccl"):
         x, cur = x_in, 0
         if p2p:
             for f_qkv, f_o, f_gu, f_down in p2p_launch:
-                f_qkv(x)
-                f_o(buf["q"])
-                f_gu(buf["o"])
-                f_down(buf["gate"])
+                f_qkv(x, flags)
+                f_o(buf["q"], flags)
+                f_gu(buf["o"], flags)
+                f_down(buf["gate"], flags)
                 launches[0] += 4
                 x, cur = hs[cur], 1 - cur
             return x
@@ -402,7 +402,7 @@ def run_ours(args):
                        "fusion": "q+k+v and gate+up each in one launch (vptq_b200_quant_gemv_multi)" if
                                  not os.environ.get("BENCH_NO_FUSE") else "one launch per linear",
                        "launch": ("one CUDA graph per token" if use_graph else "eager launches") +
-                                 ", PDL " + ("off" if (args.no_pdl or world > 1) else "on")},
+                                 ", PDL " + ("off" if (args.no_pdl or (world > 1 and tp_mode != "p2p")) else "on")},
             "gpu_launches": n_launch * args.steps,
             "e2e": {"value": round(1e3 / (ms_e2e / e2e_steps), 2), "unit": "tokens/s",
                     "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2,

@@ -229,10 +229,6 @@ int vptq_b200_quant_gemv_multi_tp(int32_t n, const vptq_linear_desc* const* desc
         return VPTQ_ERR_INVALID;
       }
   }
-  if (flags & VPTQ_FLAG_PDL) {
-    set_error("quant_gemv_multi_tp: programmatic dependent launch is not supported together with flag waits");
-    return VPTQ_ERR_UNSUPPORTED;
-  }
   return gemv_multi_launch(n, descs, x, x_stride, ys, y_strides, tokens, flags, static_cast<cudaStream_t>(stream), tp);
 }
 

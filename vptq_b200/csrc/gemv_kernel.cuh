@@ -436,11 +436,13 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
   T* y = reinterpret_cast<T*>(p.y);
 
   // the one place y is written: locally and, under tensor parallelism, into every peer's buffer
+  bool stored_to_peers = false;
   auto store_y = [&](int t, int o, float v) {
     const T hv = DT<T>::from_float(v);
     const int64_t off = int64_t(t) * p.y_stride + o;
     y[off] = hv;
     if (p.tp_world > 1) {
+      stored_to_peers = true;
 #pragma unroll 1
       for (int r = 0; r < p.tp_world; ++r)
         if (r != p.tp_rank) reinterpret_cast<T*>(p.tp_peer_y[r])[off] = hv;
@@ -648,7 +650,7 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
 
   // -------- tensor-parallel hand-off: publish this launch's epoch on every peer ------------------
   if (p.tp_world > 1) {
-    __threadfence_system();  // this thread's peer stores are visible system-wide
+    if (stored_to_peers) __threadfence_system();  // this thread's peer stores are visible system-wide
     __syncthreads();
     if (tid == 0) {
       const uint32_t prev = atomicAdd(p.tp_done + p.tp_slot, 1u);

@@ -258,11 +258,12 @@ class FusedGemvTP:
         self.y_arr = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
         self.stride_arr = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
 
-    def __call__(self, x2d: torch.Tensor) -> None:
+    def __call__(self, x2d: torch.Tensor, flags: int = 0) -> None:
         dev = x2d.device
         with torch.cuda.device(dev):
             rc = lib().vptq_b200_quant_gemv_multi_tp(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0), self.y_arr,
-                                                     self.stride_arr, x2d.shape[0], ctypes.byref(self.ex), 0, _stream(dev))
+                                                     self.stride_arr, x2d.shape[0], ctypes.byref(self.ex), flags,
+                                                     _stream(dev))
         check(rc, "vptq_b200_quant_gemv_multi_tp")
 
 
