@@ -295,7 +295,19 @@ def run_ours(args):
     stack = build_stack(m, q, device, rank, world, dtype)
     _log("weights built")
     tp_mode = args.tp_mode if world > 1 else "none"
-    x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags, tp_mode)
+    if tp_mode == "p2p":
+        # peer-mapped activations need symmetric memory; every rank must take the same decision
+        ok = torch.ones(1, device=device)
+        try:
+            x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags, "p2p")
+        except Exception as e:  # noqa: BLE001
+            _log(f"p2p exchange unavailable ({e!r}); falling back to NCCL all-reduce")
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0.0:
+            tp_mode = "nccl"
+    if tp_mode != "p2p":
+        x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags, tp_mode)
     x_host = torch.randn(1, m["hidden"]).to(dtype).pin_memory()
     y_host = torch.empty(1, m["hidden"], dtype=dtype).pin_memory()
 
