@@ -636,14 +636,45 @@ __device__ __forceinline__ void gemv_body(const GemvParams& p, uint8_t* smem, co
   if (pl.cluster && chunk == 0) {
     mbar_wait(part_bar, 0);  // all nch * nrows_cta * NT * V partial sums have landed
     stamp(9);
-    const int n = nrows_cta * NT * V;
-    for (int i = tid; i < n; i += blockDim.x) {
-      const int e = i % V, t = (i / V) % NT, krow = i / (V * NT);
-      const int o = (cta_in_chunk + pl.cpc * krow) * V + e;
-      if (o < p.O) {
-        float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
-        for (int ch = 0; ch < pl.nch; ++ch) v += s_part[((krow * pl.nch + ch) * NT + t) * V + e];
-        store_y(t, o, v);
+    if constexpr (V == 8) {
+      // one thread per (row, token): its 8 outputs leave as ONE 16-byte store (locally and, under
+      // tensor parallelism, per peer: 8x fewer NVLink packets than element-wise stores)
+      for (int i = tid; i < nrows_cta * NT; i += blockDim.x) {
+        const int t = i % NT, krow = i / NT;
+        const int o0 = (cta_in_chunk + pl.cpc * krow) * V;
+        float v[V];
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          v[e] = (bias && o0 + e < p.O) ? DT<T>::to_float(bias[o0 + e]) : 0.f;
+          for (int ch = 0; ch < pl.nch; ++ch) v[e] += s_part[((krow * pl.nch + ch) * NT + t) * V + e];
+        }
+        const int64_t off = int64_t(t) * p.y_stride + o0;
+        if (o0 + V <= p.O && ((reinterpret_cast<uintptr_t>(y + off) & 15u) == 0)) {
+          const uint4 pk = make_uint4(DT<T>::pack2(v[0], v[1]), DT<T>::pack2(v[2], v[3]), DT<T>::pack2(v[4], v[5]),
+                                      DT<T>::pack2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(y + off) = pk;
+          if (p.tp_world > 1) {
+            stored_to_peers = true;
+#pragma unroll 1
+            for (int r = 0; r < p.tp_world; ++r)
+              if (r != p.tp_rank) *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.tp_peer_y[r]) + off) = pk;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < V; ++e)
+            if (o0 + e < p.O) store_y(t, o0 + e, v[e]);
+        }
+      }
+    } else {
+      const int n = nrows_cta * NT * V;
+      for (int i = tid; i < n; i += blockDim.x) {
+        const int e = i % V, t = (i / V) % NT, krow = i / (V * NT);
+        const int o = (cta_in_chunk + pl.cpc * krow) * V + e;
+        if (o < p.O) {
+          float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
+          for (int ch = 0; ch < pl.nch; ++ch) v += s_part[((krow * pl.nch + ch) * NT + t) * V + e];
+          store_y(t, o, v);
+        }
       }
     }
   }
