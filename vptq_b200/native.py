@@ -228,6 +228,10 @@ class FusedGemv:
 
     def __init__(self, descs, ys):
         n = len(descs)
+        if not 1 <= n <= MAX_FUSED or len(ys) != n:
+            raise RuntimeError(f"FusedGemv takes 1..{MAX_FUSED} layers with one output each")
+        if any(d.in_features != descs[0].in_features or d.dtype != descs[0].dtype for d in descs):
+            raise RuntimeError("FusedGemv: the layers must read the same x (same in_features and dtype)")
         self.n, self.descs, self.ys = n, list(descs), list(ys)
         self.desc_arr = (ctypes.POINTER(LinearDesc) * n)(*[ctypes.pointer(d) for d in descs])
         self.y_arr = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
