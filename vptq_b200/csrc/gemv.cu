@@ -24,9 +24,9 @@ std::mutex g_mutex;
 std::unordered_set<const void*> g_attr_done;
 std::map<std::tuple<const void*, int, int, int>, int> g_max_clusters;
 
-// Developer tuning knobs (not part of the ABI): VPTQ_B200_GEMV_TUNE="nb=4,rep=1,stages=2,seg=512,warps=16,cpg=4"
+// Developer tuning knobs (not part of the ABI): VPTQ_B200_GEMV_TUNE="rep=1,stages=2,seg=512,warps=16,cpg=4,wsplit=2,cluster=0"
 struct Tune {
-  int nb = 0, rep = -1, stages = 0, seg = 0, warps = 0, cpg = 0, cluster = -1, wsplit = 0;
+  int rep = -1, stages = 0, seg = 0, warps = 0, cpg = 0, cluster = -1, wsplit = 0;
 };
 const Tune& tune() {
   static Tune t = [] {
@@ -37,8 +37,8 @@ const Tune& tune() {
       const char* p = std::strstr(e, key);
       if (p) dst = std::atoi(p + std::strlen(key));
     };
-    get("nb=", r.nb), get("rep=", r.rep), get("stages=", r.stages), get("seg=", r.seg), get("warps=", r.warps),
-        get("cpg=", r.cpg), get("cluster=", r.cluster), get("wsplit=", r.wsplit);
+    get("rep=", r.rep), get("stages=", r.stages), get("seg=", r.seg), get("warps=", r.warps), get("cpg=", r.cpg),
+        get("cluster=", r.cluster), get("wsplit=", r.wsplit);
     return r;
   }();
   return t;
@@ -133,7 +133,6 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
   for (const Attempt& a : attempts) {
     if (a.main_smem && !main_fits) continue;
     if (tn.warps && a.warps != tn.warps) continue;
-    const bool async = false;
 
     // ---- column chunks (cpg per codebook group, multiples of 128 columns) x warps per row -------
     // A CTA streams rows_cta * cc fields; its nwarps/wsplit row slots work in parallel, each row
@@ -191,7 +190,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
     pl.main_rep = a.main_smem ? main_rep_smem : 1;
 
     // ---- shared memory carve-up ----------------------------------------------------------------
-    auto carve = [&](int warps, int stages, int nb, int res_rep) -> size_t {
+    auto carve = [&](int warps, int stages, int res_rep) -> size_t {
       pl.res_rep = res_rep;
       size_t off = 0;
       pl.off_bars = uint32_t(off);
@@ -220,29 +219,19 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
       off += align_up((res_rep > 1 ? res_bytes : 0) + (a.main_smem && pl.main_rep > 1 ? main_bytes : 0), 128);
       pl.off_ring = uint32_t(off);
       off += align_up(size_t(warps) * stages * pl.stage_bytes, 128);
-      (void)nb;
       return off;
     };
-    // what to shed, in order, until the layout fits
-    struct Shape { int stages, nb, rep; };
+    // what to shed, in order, until the layout fits.  L2-gather layers: a small footprint leaves
+    // more of the 256 KB L1/shared array to cache codebook lines (measured: 2 stages beat 4);
+    // smem-resident codebooks take the deeper ring.
+    struct Shape { int stages, rep; };
     std::vector<Shape> shapes;
-    if (async) {
-      // the gather ring (memory-level parallelism on the L2 tier) is worth more than the
-      // conflict-free residual table or a deeper index ring
-      for (int nb : {4, 3, 2})
-        for (int rep : {res_rep_max, 1})
-          for (int st : {3, 2}) shapes.push_back({st, nb, rep});
-    } else {
-      // L2-gather layers: a small footprint leaves more of the 256 KB L1/shared array to cache
-      // codebook lines (measured: 2 stages beat 4); smem-resident codebooks take the deeper ring
-      for (int st : (a.main_smem ? std::vector<int>{4, 3, 2} : std::vector<int>{2}))
-        for (int rep : {res_rep_max, 1}) shapes.push_back({st, 0, rep});
-    }
+    for (int st : (a.main_smem ? std::vector<int>{4, 3, 2} : std::vector<int>{2}))
+      for (int rep : {res_rep_max, 1}) shapes.push_back({st, rep});
     bool placed = false;
     for (const Shape& sh : shapes) {
-      if (tn.nb && async && sh.nb != tn.nb) continue;
       if (tn.stages && sh.stages != tn.stages) continue;
-      const size_t need = carve(a.warps, sh.stages, sh.nb, sh.rep);
+      const size_t need = carve(a.warps, sh.stages, sh.rep);
       if (need <= size_t(smem_limit)) {
         pl.threads = a.warps * 32, pl.stages = sh.stages, pl.smem_bytes = uint32_t(need);
         placed = true;
