@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define VPTQ_B200_ABI_VERSION 3
+#define VPTQ_B200_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define VPTQ_B200_API __attribute__((visibility("default")))
@@ -116,6 +116,24 @@ typedef struct vptq_linear_desc {
      weight_scale[perm[c]] -- lets the decode kernel load them without waiting for perm. */
   const void* weight_scale_q; /* [I] or NULL */
   const void* weight_bias_q;  /* [I] or NULL */
+
+  /* Optional second load-time derivative: the SAME indices re-bucketed for the decode kernel that
+     keeps a 128 KiB slice of a large main codebook in each SM's shared memory (NULL = not provided:
+     the packed words above are decoded directly; results agree up to fp32 summation order).
+     Eligible layers: vector_len 8, one codebook group, no outlier columns, K a multiple of 8192
+     (NS = K / 8192 slices, 2 <= NS <= 8), Kr <= 256; used for single-token calls.
+     For slice s and index row r, list (s, r) holds the fields of row r whose main index lies in
+     [8192 s, 8192 (s+1)), in any order (the builder orders them so that 8 consecutive entries hit 8
+     different 16-byte bank groups), padded with null entries to whole steps of 32 entries.  Lists
+     are stored slice-major, one step record after the other:
+       sliced_offsets[s*Ro + r]  first step of list (s, r); sliced_offsets[NS*Ro] = number of steps
+       sliced_stream             per step: 32 little-endian words  (main index & 8191) | column << 16
+                                 (null entry: column = in_features, an x' slot the kernel keeps at 0),
+                                 then -- only when Kr > 0 -- 32 bytes, the residual indices of the
+                                 same 32 fields: 160 (128) bytes per step, 16-byte aligned.
+     vptq_b200.native.make_desc(sliced=True) builds both. */
+  const void* sliced_stream;
+  const uint32_t* sliced_offsets;
 } vptq_linear_desc;
 
 typedef enum vptq_op {

@@ -147,8 +147,8 @@ def test_c_abi_exports_every_declared_symbol():
 
 def test_c_abi_struct_layout_matches_header():
     from vptq_b200 import native
-    # 2 + 10 int32 (48 B) then 15 pointer/int64 slots
-    assert ctypes.sizeof(native.LinearDesc) == 48 + 15 * 8
+    # 2 + 10 int32 (48 B) then 17 pointer/int64 slots
+    assert ctypes.sizeof(native.LinearDesc) == 48 + 17 * 8
     assert native.LinearDesc.indices.offset == 48
 
 

@@ -81,4 +81,4 @@ for cname in only:
                                       Gfields_per_s=round(ro * i / us / 1e3, 1))
         print(f"{cname}/{name}: {out[f'{cname}/{name}']}", flush=True)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "gemv_shapes.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "gpurun_out", f"gemv_shapes{os.environ.get('PROFILE_TAG', '')}.json"), "w"), indent=1)

@@ -80,6 +80,24 @@ void gemv_set_profile_buffer(void* dev_ptr);
 int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void* y, int64_t y_stride,
                 int tokens, void* workspace, size_t workspace_bytes, uint32_t flags, cudaStream_t stream);
 
+// shared launch plumbing (gemv.cu)
+int ensure_smem_attr(const void* fn, int bytes);  // opt in to `bytes` of dynamic shared memory, once per kernel
+// how many clusters of `csize` CTAs (threads, smem each) the device can hold at once; <= 0: unknown
+int max_active_clusters(const void* fn, int csize, int threads, int smem, int optin);
+int gemv_tune_sliced();  // developer knob VPTQ_B200_GEMV_TUNE="sliced=0|1" (-1: not set)
+
+// -------------------------------------------------------------------------------------------
+// decode GEMV, sliced-codebook variant (gemv_sliced.cu): one token, layers carrying the re-bucketed
+// index lists of vptq_linear_desc::sliced_*.  A cluster of NS CTAs covers a range of index rows,
+// CTA s keeps slice s of the main codebook (128 KiB) in shared memory and walks list (s, r) of its
+// rows: every codebook gather is a shared-memory access instead of an L1/L2 one.
+// -------------------------------------------------------------------------------------------
+constexpr int kMaxFusedLayers = 4;
+bool gemv_sliced_eligible(const vptq_linear_desc& d);
+// n layers reading the same x in one launch.  VPTQ_ERR_UNSUPPORTED: use the generic kernel.
+int gemv_sliced_launch(int n, const vptq_linear_desc* const* descs, const void* x, void* const* ys, uint32_t flags,
+                       cudaStream_t stream);
+
 // -------------------------------------------------------------------------------------------
 // dequant
 // -------------------------------------------------------------------------------------------

@@ -14,13 +14,16 @@ from typing import Optional
 
 import torch
 
+from . import sliced as _sliced
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvptq_b200.so")
 
 VPTQ_FP16, VPTQ_BF16 = 0, 1
 OP_GEMV, OP_DEQUANT, OP_GEMM, OP_GEMV_V2 = 0, 1, 2, 3
 FLAG_PDL = 1
-ABI_VERSION = 3
+ABI_VERSION = 4
+SLICED_DEFAULT = "1"   # VPTQ_B200_SLICED when unset
 
 EXPORTS = (
     "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
@@ -57,6 +60,7 @@ class LinearDesc(ctypes.Structure):
         ("outlier_indices", ctypes.c_void_p), ("outlier_centroids", ctypes.c_void_p),
         ("perm", ctypes.c_void_p), ("weight_scale", ctypes.c_void_p), ("weight_bias", ctypes.c_void_p),
         ("bias", ctypes.c_void_p), ("weight_scale_q", ctypes.c_void_p), ("weight_bias_q", ctypes.c_void_p),
+        ("sliced_stream", ctypes.c_void_p), ("sliced_offsets", ctypes.c_void_p),
     ]
 
 
@@ -144,12 +148,17 @@ def make_desc(*, dtype: torch.dtype, in_features: int, out_features: int, vector
               outlier_indices: Optional[torch.Tensor], outlier_centroids: Optional[torch.Tensor],
               perm: Optional[torch.Tensor], weight_scale: Optional[torch.Tensor],
               weight_bias: Optional[torch.Tensor], bias: Optional[torch.Tensor],
-              derive: bool = True) -> LinearDesc:
+              derive: bool = True, sliced: Optional[bool] = None) -> LinearDesc:
     """Describe one layer's tensors for the C ABI.  Tensors are borrowed: keep them alive.
 
     With `derive` (default) the load-time derivatives the ABI accepts are built here, once:
     weight_scale / weight_bias in quantised column order (`t[perm]`).  They hang off the returned
     descriptor (`desc._keep`) so they live as long as it does.
+
+    `sliced`: also build the slice-bucketed index lists (vptq_b200.sliced) that let single-token calls
+    of large-codebook layers gather from shared memory; costs 5 bytes per index on top of the packed
+    words.  None = the VPTQ_B200_SLICED environment variable (default on); ignored for layers the
+    sliced kernel does not cover.
     """
     if indices.dtype != torch.int32:
         raise RuntimeError("`indices` must be packed int32 words (is_indice_packed=True); "
@@ -188,6 +197,16 @@ def make_desc(*, dtype: torch.dtype, in_features: int, out_features: int, vector
         ws_q, wb_q = weight_scale[pidx].contiguous(), weight_bias[pidx].contiguous()
         d.weight_scale_q, d.weight_bias_q = ws_q.data_ptr(), wb_q.data_ptr()
         d._keep = (ws_q, wb_q)
+    if sliced is None:
+        sliced = os.environ.get("VPTQ_B200_SLICED", SLICED_DEFAULT) != "0"
+    if sliced and derive and _sliced.eligible(
+            vector_len=d.vector_len, num_centroids=d.num_centroids, num_res_centroids=d.num_res_centroids,
+            num_codebooks=d.num_codebooks, outlier_size=d.outlier_size, in_features=d.in_features):
+        stream, offs = _sliced.build_sliced(indices, num_centroids=d.num_centroids,
+                                            num_res_centroids=d.num_res_centroids, group_size=d.group_size,
+                                            out_features=d.out_features)
+        d.sliced_stream, d.sliced_offsets = stream.data_ptr(), offs.data_ptr()
+        d._keep = d._keep + (stream, offs)
     return d
 
 
