@@ -64,9 +64,16 @@ def test_gemv_matches_reference_cuda(ref, name):
                                       m.weight_scale, m.weight_bias, m.bias, L.in_features, L.out_features))
         torch.cuda.synchronize()
         y_star = vo.quant_gemm(x_np, L)
-        e_ours, e_ref, e_mut = parity_error(y_ours, y_star), parity_error(y_ref, y_star), parity_error(y_ours, y_ref)
-        print(f"{name} tokens={tokens}: ours-vs-exact {e_ours:.2e}  ref-vs-exact {e_ref:.2e}  ours-vs-ref {e_mut:.2e}")
+        e_ours = parity_error(y_ours, y_star)
         assert e_ours <= tol
+        if not np.isfinite(y_ref).all():
+            # seen on B200 for the outlier configuration: the reference kernel returns NaN on some runs
+            # (it reads memory it never wrote, so the result depends on what the allocator hands it);
+            # nothing to compare with then -- our distance to exact arithmetic is asserted above
+            print(f"{name} tokens={tokens}: ours-vs-exact {e_ours:.2e}  reference kernel output is not finite, skipped")
+            continue
+        e_ref, e_mut = parity_error(y_ref, y_star), parity_error(y_ours, y_ref)
+        print(f"{name} tokens={tokens}: ours-vs-exact {e_ours:.2e}  ref-vs-exact {e_ref:.2e}  ours-vs-ref {e_mut:.2e}")
         assert e_mut <= max(tol, 2 * e_ref), (e_mut, e_ref)
 
 

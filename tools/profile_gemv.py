@@ -21,10 +21,14 @@ cfgs = {"b24_k65536_r256": bench.QUANT,
         "b12_k4096": dict(vector_len=8, num_centroids=4096, num_res_centroids=-1),
         "b8_k256": dict(vector_len=8, num_centroids=256, num_res_centroids=-1)}
 PHASES = "--phases" in sys.argv
+ONCE = "--once" in sys.argv      # one launch per shape (for ncu --set full)
 only = [a for a in sys.argv[1:] if not a.startswith("--")] or list(cfgs)
 prof = torch.zeros(32, dtype=torch.int64, device=dev)
 NAMES = ["start", "bar_init", "issued+staged", "phaseA", "cb_wait+replicate", "pdl_wait", "phaseB+sync", "cluster_wait",
          "main(warp0)", "leader_wait", "end"]
+if os.environ.get("VPTQ_B200_SLICED", native.SLICED_DEFAULT) != "0":   # stamps of csrc/gemv_sliced.cu
+    NAMES = ["start", "loads+sync", "ring+res", "pdl_wait", "x'+sync", "slice_wait", "main(warp0)", "sync", "cluster_wait",
+             "recv_wait", "end"]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 out = {}
 for cname in only:
@@ -50,6 +54,8 @@ for cname in only:
         y = torch.empty(1, o, device=dev, dtype=torch.float16)
         native.quant_gemv(desc, x, y)
         torch.cuda.synchronize()
+        if ONCE:
+            continue
         ts = []
         for _ in range(5):
             flush.fill_(1)

@@ -95,6 +95,7 @@ int gemv_tune_sliced() { return tune().sliced; }
 // developer aid: phase-stamp buffer (device pointer) handed to every subsequent GEMV launch
 static unsigned long long* g_prof_buffer = nullptr;
 void gemv_set_profile_buffer(void* dev_ptr) { g_prof_buffer = static_cast<unsigned long long*>(dev_ptr); }
+unsigned long long* gemv_profile_buffer() { return g_prof_buffer; }
 
 int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev, GemvPlan* out, int slots_override,
                    int force_cpg) {

@@ -20,7 +20,7 @@
 //   * the NS partial sums of a row meet in the shared memory of ONE CTA of the cluster (row i of
 //     the range is owned by CTA i mod NS): st.async + mbarrier complete_tx, as in the generic
 //     kernel, but with the epilogue spread over all CTAs.  The owner sums the slices in order
-//     (deterministic) and writes y with one 16-byte store per row.
+//     (deterministic) and writes y.
 // Mathematics and reference citations: gemv_kernel.cuh (the reference's kernel is
 // csrc/kernels/quant_gemv.cuh:11-186; nothing of its structure is used here).
 #include <algorithm>
@@ -37,6 +37,7 @@ constexpr int kSliceEntries = 8192;             // main-codebook entries per sli
 constexpr int kSliceBytes = kSliceEntries * 16;  // 128 KiB
 constexpr int kSlicedWarps = 16, kSlicedThreads = kSlicedWarps * 32;
 constexpr int kSPS = 4;         // steps (32 entries each) per ring stage
+constexpr int kColBatch = 16;     // columns per thread whose loads are in flight together (x' prologue)
 constexpr int kMaxRowsCta = 256;  // rows of one cluster (bounds the offset / partial-sum tables)
 
 struct SlicedLayer {
@@ -62,6 +63,7 @@ struct SlicedParams {
   uint32_t off_bars, off_offs, off_red, off_slice, off_res, off_x, off_recv, off_wsum, off_ring;
   int res_rep, stages;
   uint32_t stage_bytes;
+  unsigned long long* prof;  // developer aid: %globaltimer stamps of the first / last CTA (or nullptr)
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -149,6 +151,15 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
   uint64_t* recv_bar = &bars[1];
   uint64_t* full = &bars[2 + warp * stages];
 
+  // phase stamps (ns) of thread 0 of the first and of the last CTA: tools/profile_gemv.py --phases
+  auto stamp = [&](int slot) {
+    if (mp.prof && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      mp.prof[(blockIdx.x == 0 ? 0 : 16) + slot] = t;
+    }
+  };
+  stamp(0);
   const uint64_t pol_stream = policy_evict_first();
   const uint64_t pol_keep = policy_evict_last();
 
@@ -177,23 +188,24 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
   {
     const T* scale_q = reinterpret_cast<const T*>(L.scale_q);
     const T one = DT<T>::from_float(1.f);
-    for (int c0 = tid; c0 < Cq; c0 += 8 * kSlicedThreads) {
-      uint32_t pc[8];
-      T sc[8];
+    for (int c0 = tid; c0 < Cq; c0 += kColBatch * kSlicedThreads) {
+      uint32_t pc[kColBatch];
+      T sc[kColBatch];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < kColBatch; ++k) {
         const int c = c0 + k * kSlicedThreads;
         pc[k] = c < Cq ? (L.perm ? uint32_t(L.perm[c]) : uint32_t(c)) : 0u;
         sc[k] = (c < Cq && scale_q) ? scale_q[c] : one;
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < kColBatch; ++k) {
         const int c = c0 + k * kSlicedThreads;
         if (c < Cq) s_xw[c] = pc[k] | (uint32_t(*reinterpret_cast<const uint16_t*>(&sc[k])) << 16);
       }
     }
   }
   __syncthreads();
+  stamp(1);
   // "this CTA runs and its barriers exist"; waited (acquire) right before the first st.async
   cluster_arrive_relaxed();
   pdl_launch_dependents();
@@ -223,28 +235,30 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
     }
   }
 
+  stamp(2);
   // -------- x arrives from the previous kernel: x'[c] = x[perm c] * scale[perm c] ------------------
   pdl_wait_prior_grid();
+  stamp(3);
   {
     const T* x = reinterpret_cast<const T*>(mp.x);
     const T* wbias_q = (s == 0) ? reinterpret_cast<const T*>(L.wbias_q) : nullptr;
     float bs = 0.f;  // slice 0 also forms sum_c x[perm c] * wbias[perm c], the weight_bias term of every row
-    for (int c0 = tid; c0 < Cq; c0 += 8 * kSlicedThreads) {
-      uint32_t w[8];
-      T xv[8], wb[8];
+    for (int c0 = tid; c0 < Cq; c0 += kColBatch * kSlicedThreads) {
+      uint32_t w[kColBatch];
+      T xv[kColBatch], wb[kColBatch];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < kColBatch; ++k) {
         const int c = c0 + k * kSlicedThreads;
         w[k] = c < Cq ? s_xw[c] : 0u;  // own slots only: no barrier since they were written
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < kColBatch; ++k) {
         const int c = c0 + k * kSlicedThreads;
         xv[k] = x[w[k] & 0xffffu];
         wb[k] = (wbias_q && c < Cq) ? wbias_q[c] : DT<T>::from_float(0.f);
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
+      for (int k = 0; k < kColBatch; ++k) {
         const int c = c0 + k * kSlicedThreads;
         if (c < Cq) {
           const uint16_t sb = uint16_t(w[k] >> 16);
@@ -266,7 +280,9 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
     for (int w = 0; w < kSlicedWarps; ++w) v += s_red[w];
     s_red[kSlicedWarps] = v;  // read after the post-loop barrier
   }
+  stamp(4);
   mbar_wait(slice_bar, 0);
+  stamp(5);
 
   // -------- main loop ---------------------------------------------------------------------------
   if (nstage > 0) {
@@ -345,10 +361,13 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
     }
     flush();
   }
+  stamp(6);  // warp 0 finished its run
   __syncthreads();
+  stamp(7);
 
   // -------- reduction over the slices: row i of the range goes to CTA i mod ns ---------------------
   cluster_wait();  // every CTA of the cluster runs and has armed its barrier
+  stamp(8);
   {
     const float cbias = (s == 0) ? s_red[kSlicedWarps] : 0.f;
     const uint32_t recv0 = smem_u32(s_recv), bar0 = smem_u32(recv_bar);
@@ -368,26 +387,21 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
   }
   if (nown > 0) {
     mbar_wait(recv_bar, 0);  // ns * nown * 8 partial sums have landed
+    stamp(9);
     const T* bias = reinterpret_cast<const T*>(L.bias);
     T* y = reinterpret_cast<T*>(L.y);
-    for (int j = tid; j < nown; j += kSlicedThreads) {
-      const int o0 = (r0 + j * ns + s) * 8;
-      float v[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        v[e] = (bias && o0 + e < L.O) ? DT<T>::to_float(bias[o0 + e]) : 0.f;
-        for (int sl = 0; sl < ns; ++sl) v[e] += s_recv[(sl * nown_max + j) * 8 + e];
-      }
-      if (o0 + 8 <= L.O && (reinterpret_cast<uintptr_t>(y + o0) & 15u) == 0) {
-        *reinterpret_cast<uint4*>(y + o0) = make_uint4(DT<T>::pack2(v[0], v[1]), DT<T>::pack2(v[2], v[3]),
-                                                       DT<T>::pack2(v[4], v[5]), DT<T>::pack2(v[6], v[7]));
-      } else {
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (o0 + e < L.O) y[o0 + e] = DT<T>::from_float(v[e]);
+    // one thread per output value: the 8 values of a row leave as 8 adjacent 2-byte stores
+    for (int i = tid; i < nown * 8; i += kSlicedThreads) {
+      const int j = i >> 3, e = i & 7;
+      const int o = (r0 + j * ns + s) * 8 + e;
+      if (o < L.O) {
+        float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
+        for (int sl = 0; sl < ns; ++sl) v += s_recv[(sl * nown_max + j) * 8 + e];
+        y[o] = DT<T>::from_float(v);
       }
     }
   }
+  stamp(10);
 }
 
 using SlicedKernelFn = void (*)(const SlicedParams);
@@ -517,7 +531,7 @@ int gemv_sliced_launch(int n, const vptq_linear_desc* const* descs, const void* 
     return VPTQ_ERR_UNSUPPORTED;
   }
 
-  mp.n = n, mp.ns = ns, mp.x = x;
+  mp.n = n, mp.ns = ns, mp.x = x, mp.prof = gemv_profile_buffer();
   uint32_t begin = 0;
   for (int l = 0; l < n; ++l) {
     const vptq_linear_desc& d = *descs[l];

@@ -76,6 +76,7 @@ int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x
                       const int64_t* y_strides, int tokens, uint32_t flags, cudaStream_t stream,
                       const vptq_tp_exchange* tp = nullptr);
 void gemv_set_profile_buffer(void* dev_ptr);
+unsigned long long* gemv_profile_buffer();
 // Launches ceil(tokens / plan.nt) passes.
 int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void* y, int64_t y_stride,
                 int tokens, void* workspace, size_t workspace_bytes, uint32_t flags, cudaStream_t stream);
