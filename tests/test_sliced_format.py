@@ -115,13 +115,27 @@ def test_run_partition_covers_every_step_once(seed):
     offs = np.concatenate([[int(rng.integers(0, 1000))], lens]).cumsum()
     T0, TT = int(offs[0]), int(offs[-1] - offs[0])
     pieces = _partition([int(v) for v in offs])
+    _check_pieces(offs, pieces)
+
+
+def _check_pieces(offs, pieces):
+    nrows, T0, TT = len(offs) - 1, int(offs[0]), int(offs[-1] - offs[0])
     for row in range(nrows):
         a, b = int(offs[row]) - T0, int(offs[row + 1]) - T0
         total = 0
         if b > a:                                                  # the epilogue's fw / lw formulas
             fw, lw = ((a + 1) * 16 - 1) // TT, (b * 16 - 1) // TT
             for w in range(fw, lw + 1):
+                if row + w not in pieces:                          # a warp with an empty run: the kernel
+                    assert TT * w // 16 == TT * (w + 1) // 16      # zero-fills the piece table for these
+                    continue
                 r, ww, n = pieces[row + w]
                 assert (r, ww) == (row, w)
                 total += n
         assert total == b - a
+
+
+@pytest.mark.parametrize("lens", [[9], [1], [0, 3, 0], [5, 0, 0, 7], [2, 2, 2], [15], [16], [17, 1]])
+def test_run_partition_with_fewer_steps_than_warps(lens):
+    offs = np.concatenate([[7], lens]).cumsum()
+    _check_pieces(offs, _partition([int(v) for v in offs]))

@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
   // -------- x-independent column data: list offsets of this CTA's rows; perm and scale of every
   // quantised column, parked in the x' array as (perm | scale bits << 16) until x arrives ---------
   for (int i = tid; i <= nrows; i += kSlicedThreads) s_offs[i] = L.offsets[size_t(s) * L.Ro + r0 + i];
+  // row pieces of warps whose run is empty (fewer steps than warps) are read as zero by the epilogue
+  for (int i = tid; i < (nrows + kSlicedWarps) * 8; i += kSlicedThreads) s_wsum[i] = 0.f;
   {
     const T* scale_q = reinterpret_cast<const T*>(L.scale_q);
     const T one = DT<T>::from_float(1.f);
