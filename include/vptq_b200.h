@@ -166,6 +166,20 @@ VPTQ_B200_API int vptq_b200_quant_gemv(const vptq_linear_desc* desc, const void*
                          size_t workspace_bytes, uint32_t flags, void* stream);
 
 /*
+ * Host-side builder of the sliced index lists of ONE layer (vptq_linear_desc::sliced_stream /
+ * ::sliced_offsets) for hosts that do not use vptq_b200.native: plain CPU code, no GPU work.  Reads
+ * the packed index words [Ro][index_stride_row] of a one-codebook layer from HOST memory and writes
+ * HOST buffers the caller uploads (16-byte aligned on the device).  offsets_out must hold
+ * (K / 8192) * ceil(O / 8) + 1 words.  With stream_out == NULL only offsets_out and *steps_out are
+ * produced (sizing call: stream bytes = *steps_out * (Kr > 0 ? 160 : 128)).  Byte-identical to the
+ * lists vptq_b200.sliced.build_sliced produces on the GPU.
+ */
+VPTQ_B200_API int vptq_b200_sliced_build_host(const int32_t* indices_host, int64_t index_stride_row,
+                                              int32_t out_features, int32_t group_size, int32_t num_centroids,
+                                              int32_t num_res_centroids, void* stream_out, size_t stream_capacity,
+                                              uint32_t* offsets_out, size_t* steps_out);
+
+/*
  * Decode path, horizontally fused: up to 4 layers that read the SAME x (q/k/v, gate/up of a
  * decoder layer) in ONE launch -- y_l = x W_l^T + bias_l for every l.  No reference counterpart
  * (the reference launches each VQuantLinear separately); identical results to n separate

@@ -139,3 +139,25 @@ def _check_pieces(offs, pieces):
 def test_run_partition_with_fewer_steps_than_warps(lens):
     offs = np.concatenate([[7], lens]).cumsum()
     _check_pieces(offs, _partition([int(v) for v in offs]))
+
+
+@pytest.mark.parametrize("c", CASES)
+def test_c_abi_host_builder_is_byte_identical(c):
+    """vptq_b200_sliced_build_host (plain CPU code in the shared library) == the tensor builder."""
+    import ctypes
+    from vptq_b200 import native
+    L, stream, offs = _build(c)
+    lib = native.lib()
+    ind = np.ascontiguousarray(L.indices[0])
+    Ro, NS = (c["O"] + 7) // 8, c["K"] // 8192
+    offs_c = np.zeros(NS * Ro + 1, dtype=np.uint32)
+    steps = ctypes.c_size_t(0)
+    args = (ind.ctypes.data, ind.shape[1], c["O"], c["I"], c["K"], c["Kr"])
+    assert lib.vptq_b200_sliced_build_host(*args, None, 0, offs_c.ctypes.data, ctypes.byref(steps)) == 0
+    assert steps.value == stream.shape[0]
+    out = np.zeros(steps.value * stream.shape[1], dtype=np.uint8)
+    assert lib.vptq_b200_sliced_build_host(*args, out.ctypes.data, out.size, offs_c.ctypes.data, ctypes.byref(steps)) == 0
+    assert np.array_equal(offs_c.astype(np.int64), offs.numpy().astype(np.int64))
+    assert np.array_equal(out, stream.numpy().reshape(-1))
+    # too small a buffer is refused, not overrun
+    assert lib.vptq_b200_sliced_build_host(*args, out.ctypes.data, 16, offs_c.ctypes.data, ctypes.byref(steps)) == -3

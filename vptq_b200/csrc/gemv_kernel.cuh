@@ -708,7 +708,7 @@ __global__ void __launch_bounds__(512, 1) gemv_kernel(const __grid_constant__ Ge
 // the concatenation of the layers' own grids (each planned for its share of the SMs); a CTA finds
 // its layer from blockIdx.x and then runs the ordinary per-layer body.  One launch, one prologue
 // latency, no idle SMs behind a small layer.
-constexpr int kMaxFused = 4;
+constexpr int kMaxFused = kMaxFusedLayers;  // kernels.h
 struct GemvMultiParams {
   int n;
   uint32_t grid_begin[kMaxFused + 1];  // layer l owns blocks [grid_begin[l], grid_begin[l+1])

@@ -29,6 +29,7 @@ EXPORTS = (
     "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
     "vptq_b200_dequant", "vptq_b200_quant_gemm", "vptq_b200_quant_gemv_v2", "vptq_b200_linear_host",
     "vptq_b200_debug_phase_stamps", "vptq_b200_quant_gemv_multi", "vptq_b200_quant_gemv_multi_tp",
+    "vptq_b200_sliced_build_host",
 )
 
 MAX_FUSED, MAX_RANKS = 4, 8
@@ -99,6 +100,8 @@ def lib() -> ctypes.CDLL:
         L.vptq_b200_quant_gemv_multi_tp.argtypes = [i32, ctypes.POINTER(dp), vp, i64, ctypes.POINTER(vp),
                                                     ctypes.POINTER(i64), i32, ctypes.POINTER(TpExchange), u32, vp]
         L.vptq_b200_quant_gemv_multi_tp.restype = ctypes.c_int
+        L.vptq_b200_sliced_build_host.argtypes = [vp, i64, i32, i32, i32, i32, vp, sz, vp, ctypes.POINTER(sz)]
+        L.vptq_b200_sliced_build_host.restype = ctypes.c_int
         L.vptq_b200_debug_phase_stamps.argtypes = [vp]
         L.vptq_b200_debug_phase_stamps.restype = None
         for f in ("vptq_b200_quant_gemv", "vptq_b200_quant_gemm", "vptq_b200_dequant", "vptq_b200_quant_gemv_v2",
