@@ -190,6 +190,14 @@ VPTQ_B200_API int vptq_b200_quant_gemv_multi(int32_t n, const vptq_linear_desc* 
                                              int64_t x_stride, void* const* ys, const int64_t* y_strides,
                                              int32_t tokens, uint32_t flags, void* stream);
 
+/* Same, with a workspace (first 256 KiB zero at rest, size >= the sum of vptq_b200_workspace_bytes(desc_l,
+ * tokens, VPTQ_OP_GEMV) over the layers): lets the library pick kernel variants that reduce through
+ * global memory.  Results are identical to vptq_b200_quant_gemv_multi. */
+VPTQ_B200_API int vptq_b200_quant_gemv_multi_ws(int32_t n, const vptq_linear_desc* const* descs, const void* x,
+                                                int64_t x_stride, void* const* ys, const int64_t* y_strides,
+                                                int32_t tokens, void* workspace, size_t workspace_bytes,
+                                                uint32_t flags, void* stream);
+
 /*
  * Tensor-parallel decode with the exchange fused into the kernel (no NCCL call, no memset):
  * every rank passes pointers to the SAME y slice inside every rank's full-width output buffer

@@ -1,5 +1,6 @@
 // extern "C" surface of libvptq_b200.so: argument validation, error reporting, dispatch.
 // Declarations and the mapping to the reference's pybind11 functions: include/vptq_b200.h.
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -167,7 +168,7 @@ size_t vptq_b200_workspace_bytes(const vptq_linear_desc* desc, int32_t tokens, i
       const DeviceInfo* dev = device_info();
       GemvPlan pl;
       if (gemv_make_plan(*desc, tokens, dev ? *dev : b200, &pl)) return 0;
-      return pl.ws_counters_bytes + pl.ws_partials_bytes;
+      return std::max(pl.ws_counters_bytes + pl.ws_partials_bytes, gemv_sliced_workspace_bytes(*desc));
     }
     case VPTQ_OP_DEQUANT: return dequant_workspace_bytes(*desc);
     case VPTQ_OP_GEMM: return gemm_workspace_bytes(*desc, tokens);
@@ -202,6 +203,24 @@ int vptq_b200_quant_gemv_multi(int32_t n, const vptq_linear_desc* const* descs, 
     }
   }
   return gemv_multi_launch(n, descs, x, x_stride, ys, y_strides, tokens, flags, static_cast<cudaStream_t>(stream));
+}
+
+int vptq_b200_quant_gemv_multi_ws(int32_t n, const vptq_linear_desc* const* descs, const void* x, int64_t x_stride,
+                                  void* const* ys, const int64_t* y_strides, int32_t tokens, void* workspace,
+                                  size_t workspace_bytes, uint32_t flags, void* stream) {
+  if (!descs || !x || !ys || !y_strides || n < 1) {
+    set_error("quant_gemv_multi_ws: NULL argument");
+    return VPTQ_ERR_INVALID;
+  }
+  for (int l = 0; l < n; ++l) {
+    if (int rc = validate(descs[l], l == 0)) return rc;
+    if (!ys[l] || y_strides[l] < descs[l]->out_features || x_stride < descs[l]->in_features) {
+      set_error("quant_gemv_multi_ws: bad y / stride for layer %d", l);
+      return VPTQ_ERR_INVALID;
+    }
+  }
+  return gemv_multi_launch(n, descs, x, x_stride, ys, y_strides, tokens, flags, static_cast<cudaStream_t>(stream), nullptr,
+                           workspace, workspace_bytes);
 }
 
 int vptq_b200_quant_gemv_multi_tp(int32_t n, const vptq_linear_desc* const* descs, const void* x, int64_t x_stride,

@@ -350,7 +350,7 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
   if (tokens == 1 && gemv_tune_sliced() != 0 && gemv_sliced_eligible(d)) {
     const vptq_linear_desc* dp = &d;
     void* yp = y;
-    const int rc = gemv_sliced_launch(1, &dp, x, &yp, flags, stream);
+    const int rc = gemv_sliced_launch(1, &dp, x, &yp, flags, stream, workspace, workspace_bytes);
     if (rc != VPTQ_ERR_UNSUPPORTED) return rc;
   }
   GemvPlan pl;
@@ -388,7 +388,7 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
 // needs the global-memory split-K variant) VPTQ_ERR_UNSUPPORTED tells the caller to launch separately.
 int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x, int64_t x_stride, void* const* ys,
                       const int64_t* y_strides, int tokens, uint32_t flags, cudaStream_t stream,
-                      const vptq_tp_exchange* tp) {
+                      const vptq_tp_exchange* tp, void* workspace, size_t workspace_bytes) {
   const DeviceInfo* dev = device_info();
   if (!dev) return VPTQ_ERR_CUDA;
   if (n < 1 || n > kMaxFused || tokens < 1 || tokens > 2) {
@@ -399,7 +399,7 @@ int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x
     bool all = true;
     for (int l = 0; l < n; ++l) all = all && gemv_sliced_eligible(*descs[l]);
     if (all) {
-      const int rc = gemv_sliced_launch(n, descs, x, ys, flags, stream);
+      const int rc = gemv_sliced_launch(n, descs, x, ys, flags, stream, workspace, workspace_bytes);
       if (rc != VPTQ_ERR_UNSUPPORTED) return rc;
     }
   }

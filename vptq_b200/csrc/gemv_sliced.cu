@@ -51,7 +51,8 @@ struct SlicedLayer {
   const void* bias;
   void* y;
   int Cq, O, Ro, Kr;
-  int ncl;  // clusters working on this layer
+  int ncl;        // clusters (CTA groups) working on this layer
+  int part_row0;  // global-reduce variant: first row of this layer in the partial-sum table
 };
 
 struct SlicedParams {
@@ -64,6 +65,10 @@ struct SlicedParams {
   int res_rep, stages;
   uint32_t stage_bytes;
   unsigned long long* prof;  // developer aid: %globaltimer stamps of the first / last CTA (or nullptr)
+  // global-reduce variant (CLUSTER = false): the NS CTAs of a group are ordinary CTAs; their per-row sums
+  // meet in `part` [row][slice][8] and the last CTA of the group to arrive (counter) writes y
+  float* part;
+  uint32_t* counters;  // one per group (blockIdx.x / ns), zero at rest
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -117,7 +122,7 @@ __device__ __forceinline__ void fma_entry8(float (&acc)[8], float xv, const uint
   }
 }
 
-template <typename T, bool RES>
+template <typename T, bool RES, bool CLUSTER>
 __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __grid_constant__ SlicedParams mp) {
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr uint32_t REC = RES ? 160u : 128u;  // bytes per step record
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
         tma_bulk_g2s(s_slice + off, src + off, 32768u, slice_bar, pol_keep);
     }
     // owner side of the reduction: every slice delivers 8 floats per owned row with st.async
-    if (tid == 1 && nown > 0) mbar_arrive_expect_tx(recv_bar, uint32_t(ns * nown * 8) * 4u);
+    if (CLUSTER && tid == 1 && nown > 0) mbar_arrive_expect_tx(recv_bar, uint32_t(ns * nown * 8) * 4u);
   }
   // residual codebook (<= 256 entries of 16 bytes): one entry per thread, stored res_rep times below
   uint4 res_entry = make_uint4(0u, 0u, 0u, 0u);
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
   __syncthreads();
   stamp(1);
   // "this CTA runs and its barriers exist"; waited (acquire) right before the first st.async
-  cluster_arrive_relaxed();
+  if constexpr (CLUSTER) cluster_arrive_relaxed();
   pdl_launch_dependents();
 
   // -------- this warp's run of steps: an equal share of the CTA's contiguous step range -------------
@@ -367,39 +372,81 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
   __syncthreads();
   stamp(7);
 
-  // -------- reduction over the slices: row i of the range goes to CTA i mod ns ---------------------
-  cluster_wait();  // every CTA of the cluster runs and has armed its barrier
-  stamp(8);
-  {
+  if constexpr (CLUSTER) {
+    // -------- reduction over the slices: row i of the range goes to CTA i mod ns ---------------------
+    cluster_wait();  // every CTA of the cluster runs and has armed its barrier
+    stamp(8);
+    {
+      const float cbias = (s == 0) ? s_red[kSlicedWarps] : 0.f;
+      const uint32_t recv0 = smem_u32(s_recv), bar0 = smem_u32(recv_bar);
+      for (int i = tid; i < nrows * 8; i += kSlicedThreads) {
+        const int row = i >> 3, e = i & 7;
+        float v = cbias;
+        const int a = int(s_offs[row]) - T0, b = int(s_offs[row + 1]) - T0;  // the row's steps, relative to the CTA
+        if (b > a) {
+          // warp of step u: the w with floor(TT w / 16) <= u < floor(TT (w+1) / 16)
+          const int fw = int((int64_t(a + 1) * kSlicedWarps - 1) / TT), lw = int((int64_t(b) * kSlicedWarps - 1) / TT);
+          for (int w = fw; w <= lw; ++w) v += s_wsum[(row + w) * 8 + e];
+        }
+        const uint32_t owner = uint32_t(row % ns), j = uint32_t(row / ns);
+        st_async_f32(mapa_shared(recv0 + ((uint32_t(s) * nown_max + j) * 8u + e) * 4u, owner), v,
+                     mapa_shared(bar0, owner));
+      }
+    }
+    if (nown > 0) {
+      mbar_wait(recv_bar, 0);  // ns * nown * 8 partial sums have landed
+      stamp(9);
+      const T* bias = reinterpret_cast<const T*>(L.bias);
+      T* y = reinterpret_cast<T*>(L.y);
+      // one thread per output value: the 8 values of a row leave as 8 adjacent 2-byte stores
+      for (int i = tid; i < nown * 8; i += kSlicedThreads) {
+        const int j = i >> 3, e = i & 7;
+        const int o = (r0 + j * ns + s) * 8 + e;
+        if (o < L.O) {
+          float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
+          for (int sl = 0; sl < ns; ++sl) v += s_recv[(sl * nown_max + j) * 8 + e];
+          y[o] = DT<T>::from_float(v);
+        }
+      }
+    }
+  } else {
+    // -------- reduction over the slices through global memory (L2): every CTA of the group parks its
+    // per-row sums, the last one to arrive adds the NS slices in order (deterministic) and writes y ---
     const float cbias = (s == 0) ? s_red[kSlicedWarps] : 0.f;
-    const uint32_t recv0 = smem_u32(s_recv), bar0 = smem_u32(recv_bar);
+    float* part = mp.part + size_t(L.part_row0 + r0) * ns * 8;
     for (int i = tid; i < nrows * 8; i += kSlicedThreads) {
       const int row = i >> 3, e = i & 7;
       float v = cbias;
-      const int a = int(s_offs[row]) - T0, b = int(s_offs[row + 1]) - T0;  // the row's steps, relative to the CTA
+      const int a = int(s_offs[row]) - T0, b = int(s_offs[row + 1]) - T0;
       if (b > a) {
-        // warp of step u: the w with floor(TT w / 16) <= u < floor(TT (w+1) / 16)
         const int fw = int((int64_t(a + 1) * kSlicedWarps - 1) / TT), lw = int((int64_t(b) * kSlicedWarps - 1) / TT);
         for (int w = fw; w <= lw; ++w) v += s_wsum[(row + w) * 8 + e];
       }
-      const uint32_t owner = uint32_t(row % ns), j = uint32_t(row / ns);
-      st_async_f32(mapa_shared(recv0 + ((uint32_t(s) * nown_max + j) * 8u + e) * 4u, owner), v,
-                   mapa_shared(bar0, owner));
+      part[(size_t(row) * ns + s) * 8 + e] = v;
     }
-  }
-  if (nown > 0) {
-    mbar_wait(recv_bar, 0);  // ns * nown * 8 partial sums have landed
-    stamp(9);
-    const T* bias = reinterpret_cast<const T*>(L.bias);
-    T* y = reinterpret_cast<T*>(L.y);
-    // one thread per output value: the 8 values of a row leave as 8 adjacent 2-byte stores
-    for (int i = tid; i < nown * 8; i += kSlicedThreads) {
-      const int j = i >> 3, e = i & 7;
-      const int o = (r0 + j * ns + s) * 8 + e;
-      if (o < L.O) {
-        float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
-        for (int sl = 0; sl < ns; ++sl) v += s_recv[(sl * nown_max + j) * 8 + e];
-        y[o] = DT<T>::from_float(v);
+    __threadfence();
+    __syncthreads();
+    uint32_t* flag = reinterpret_cast<uint32_t*>(s_red) + kSlicedWarps + 1;
+    if (tid == 0) {
+      uint32_t* ctr = mp.counters + blockIdx.x / uint32_t(ns);
+      const uint32_t prev = atomicAdd(ctr, 1u);
+      *flag = prev == uint32_t(ns - 1) ? 1u : 0u;
+      if (prev == uint32_t(ns - 1)) *ctr = 0u;  // leave the counter zeroed for the next launch
+    }
+    __syncthreads();
+    stamp(8);
+    if (*flag) {
+      __threadfence();
+      const T* bias = reinterpret_cast<const T*>(L.bias);
+      T* y = reinterpret_cast<T*>(L.y);
+      for (int i = tid; i < nrows * 8; i += kSlicedThreads) {
+        const int row = i >> 3, e = i & 7;
+        const int o = (r0 + row) * 8 + e;
+        if (o < L.O) {
+          float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
+          for (int sl = 0; sl < ns; ++sl) v += ldg_cg_f32(&part[(size_t(row) * ns + sl) * 8 + e]);
+          y[o] = DT<T>::from_float(v);
+        }
       }
     }
   }
@@ -408,9 +455,14 @@ __global__ void __launch_bounds__(kSlicedThreads, 1) gemv_sliced_kernel(const __
 
 using SlicedKernelFn = void (*)(const SlicedParams);
 
-SlicedKernelFn pick_sliced(int dtype, bool res) {
-  if (dtype == VPTQ_FP16) return res ? gemv_sliced_kernel<__half, true> : gemv_sliced_kernel<__half, false>;
-  if (dtype == VPTQ_BF16) return res ? gemv_sliced_kernel<__nv_bfloat16, true> : gemv_sliced_kernel<__nv_bfloat16, false>;
+template <typename T>
+SlicedKernelFn pick_sliced_t(bool res, bool cluster) {
+  if (cluster) return res ? gemv_sliced_kernel<T, true, true> : gemv_sliced_kernel<T, false, true>;
+  return res ? gemv_sliced_kernel<T, true, false> : gemv_sliced_kernel<T, false, false>;
+}
+SlicedKernelFn pick_sliced(int dtype, bool res, bool cluster) {
+  if (dtype == VPTQ_FP16) return pick_sliced_t<__half>(res, cluster);
+  if (dtype == VPTQ_BF16) return pick_sliced_t<__nv_bfloat16>(res, cluster);
   return nullptr;
 }
 
@@ -430,8 +482,13 @@ bool gemv_sliced_eligible(const vptq_linear_desc& d) {
   return true;
 }
 
+size_t gemv_sliced_workspace_bytes(const vptq_linear_desc& d) {
+  if (!gemv_sliced_eligible(d)) return 0;
+  return kCounterRegionBytes + size_t((d.out_features + 7) / 8) * (d.num_centroids / kSliceEntries) * 32;
+}
+
 int gemv_sliced_launch(int n, const vptq_linear_desc* const* descs, const void* x, void* const* ys, uint32_t flags,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, void* workspace, size_t workspace_bytes) {
   const DeviceInfo* dev = device_info();
   if (!dev) return VPTQ_ERR_CUDA;
   if (n < 1 || n > kMaxFusedLayers) {
@@ -450,14 +507,21 @@ int gemv_sliced_launch(int n, const vptq_linear_desc* const* descs, const void* 
   }
   const int ns = d0.num_centroids / kSliceEntries;
   const int Cq = d0.in_features;
-  SlicedKernelFn fn = pick_sliced(d0.dtype, res);
+  // Reduction variant.  Default: thread-block clusters (st.async into the owner's shared memory).
+  // VPTQ_B200_GEMV_TUNE="sliced=2" (experimental, needs a workspace): independent CTAs + a last-arriver
+  // reduction through global memory, which is not tied to the 15 co-resident 8-CTA clusters.
+  size_t part_rows = 0;
+  for (int l = 0; l < n; ++l) part_rows += size_t((descs[l]->out_features + 7) / 8);
+  const size_t ws_need = kCounterRegionBytes + part_rows * ns * 32;
+  const bool cluster = !(gemv_tune_sliced() == 2 && workspace && workspace_bytes >= ws_need);
+  SlicedKernelFn fn = pick_sliced(d0.dtype, res, cluster);
   if (!fn) return VPTQ_ERR_UNSUPPORTED;
   if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(fn), dev->smem_optin)) return rc;
 
   // ---- clusters that can run at once, shared out to the layers in proportion to their rows (all
   // lists of a launch have the same expected length): minimise the largest rows-per-cluster ---------
   int avail = dev->sm_count / ns;
-  {
+  if (cluster) {
     const int nmax = max_active_clusters(reinterpret_cast<const void*>(fn), ns, kSlicedThreads, 220 * 1024, dev->smem_optin);
     if (nmax > 0) avail = std::min(avail, nmax);
   }
@@ -535,9 +599,16 @@ int gemv_sliced_launch(int n, const vptq_linear_desc* const* descs, const void* 
 
   mp.n = n, mp.ns = ns, mp.x = x, mp.prof = gemv_profile_buffer();
   uint32_t begin = 0;
+  int part_row0 = 0;
+  if (!cluster) {
+    mp.counters = reinterpret_cast<uint32_t*>(workspace);
+    mp.part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + kCounterRegionBytes);
+  }
   for (int l = 0; l < n; ++l) {
     const vptq_linear_desc& d = *descs[l];
     SlicedLayer& L = mp.layer[l];
+    L.part_row0 = part_row0;
+    part_row0 += Ro[l];
     L.stream = reinterpret_cast<const uint8_t*>(d.sliced_stream), L.offsets = d.sliced_offsets;
     L.centroids = d.centroids, L.res_centroids = d.res_centroids;
     L.perm = d.perm, L.scale_q = d.weight_scale ? d.weight_scale_q : nullptr;
@@ -562,13 +633,16 @@ int gemv_sliced_launch(int n, const vptq_linear_desc* const* descs, const void* 
     attr[nattr].val.programmaticStreamSerializationAllowed = 1;
     ++nattr;
   }
-  attr[nattr].id = cudaLaunchAttributeClusterDimension;
-  attr[nattr].val.clusterDim.x = unsigned(ns), attr[nattr].val.clusterDim.y = 1, attr[nattr].val.clusterDim.z = 1;
-  ++nattr;
+  if (cluster) {
+    attr[nattr].id = cudaLaunchAttributeClusterDimension;
+    attr[nattr].val.clusterDim.x = unsigned(ns), attr[nattr].val.clusterDim.y = 1, attr[nattr].val.clusterDim.z = 1;
+    ++nattr;
+  }
   cfg.attrs = attr, cfg.numAttrs = unsigned(nattr);
   const cudaError_t e = cudaLaunchKernelEx(&cfg, fn, mp);
   if (e != cudaSuccess) {
-    set_error("gemv_sliced launch (grid=%u smem=%zu cluster=%d): %s", begin, need, ns, cudaGetErrorString(e));
+    set_error("gemv_sliced launch (grid=%u smem=%zu group=%d cluster=%d): %s", begin, need, ns, int(cluster),
+              cudaGetErrorString(e));
     return VPTQ_ERR_CUDA;
   }
   return 0;

@@ -74,7 +74,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
                    int force_cpg = 0);
 int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x, int64_t x_stride, void* const* ys,
                       const int64_t* y_strides, int tokens, uint32_t flags, cudaStream_t stream,
-                      const vptq_tp_exchange* tp = nullptr);
+                      const vptq_tp_exchange* tp = nullptr, void* workspace = nullptr, size_t workspace_bytes = 0);
 void gemv_set_profile_buffer(void* dev_ptr);
 unsigned long long* gemv_profile_buffer();
 // Launches ceil(tokens / plan.nt) passes.
@@ -96,8 +96,10 @@ int gemv_tune_sliced();  // developer knob VPTQ_B200_GEMV_TUNE="sliced=0|1" (-1:
 constexpr int kMaxFusedLayers = 4;
 bool gemv_sliced_eligible(const vptq_linear_desc& d);
 // n layers reading the same x in one launch.  VPTQ_ERR_UNSUPPORTED: use the generic kernel.
+// `workspace` (optional): needed only by the experimental global-memory reduction (sliced=2 tuning knob)
 int gemv_sliced_launch(int n, const vptq_linear_desc* const* descs, const void* x, void* const* ys, uint32_t flags,
-                       cudaStream_t stream);
+                       cudaStream_t stream, void* workspace = nullptr, size_t workspace_bytes = 0);
+size_t gemv_sliced_workspace_bytes(const vptq_linear_desc& d);  // 0 when the layer is not eligible
 
 // -------------------------------------------------------------------------------------------
 // dequant

@@ -29,7 +29,7 @@ EXPORTS = (
     "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
     "vptq_b200_dequant", "vptq_b200_quant_gemm", "vptq_b200_quant_gemv_v2", "vptq_b200_linear_host",
     "vptq_b200_debug_phase_stamps", "vptq_b200_quant_gemv_multi", "vptq_b200_quant_gemv_multi_tp",
-    "vptq_b200_sliced_build_host",
+    "vptq_b200_sliced_build_host", "vptq_b200_quant_gemv_multi_ws",
 )
 
 MAX_FUSED, MAX_RANKS = 4, 8
@@ -97,6 +97,9 @@ def lib() -> ctypes.CDLL:
         L.vptq_b200_quant_gemv_multi.argtypes = [i32, ctypes.POINTER(dp), vp, i64, ctypes.POINTER(vp),
                                                  ctypes.POINTER(i64), i32, u32, vp]
         L.vptq_b200_quant_gemv_multi.restype = ctypes.c_int
+        L.vptq_b200_quant_gemv_multi_ws.argtypes = [i32, ctypes.POINTER(dp), vp, i64, ctypes.POINTER(vp),
+                                                    ctypes.POINTER(i64), i32, vp, sz, u32, vp]
+        L.vptq_b200_quant_gemv_multi_ws.restype = ctypes.c_int
         L.vptq_b200_quant_gemv_multi_tp.argtypes = [i32, ctypes.POINTER(dp), vp, i64, ctypes.POINTER(vp),
                                                     ctypes.POINTER(i64), i32, ctypes.POINTER(TpExchange), u32, vp]
         L.vptq_b200_quant_gemv_multi_tp.restype = ctypes.c_int
@@ -259,13 +262,20 @@ class FusedGemv:
         self.y_arr = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
         self.stride_arr = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
         self.separate = False
+        self.with_workspace = "sliced=2" in os.environ.get("VPTQ_B200_GEMV_TUNE", "")
 
     def __call__(self, x2d: torch.Tensor, flags: int = 0) -> None:
         dev = x2d.device
         if not self.separate:
             with torch.cuda.device(dev):
-                rc = lib().vptq_b200_quant_gemv_multi(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0), self.y_arr,
-                                                      self.stride_arr, x2d.shape[0], flags, _stream(dev))
+                if self.with_workspace:   # experimental kernel variants that reduce through global memory
+                    ws = workspace(dev, sum(workspace_bytes(d, x2d.shape[0], OP_GEMV) for d in self.descs))
+                    rc = lib().vptq_b200_quant_gemv_multi_ws(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0),
+                                                             self.y_arr, self.stride_arr, x2d.shape[0], ws.data_ptr(),
+                                                             ws.numel(), flags, _stream(dev))
+                else:
+                    rc = lib().vptq_b200_quant_gemv_multi(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0),
+                                                          self.y_arr, self.stride_arr, x2d.shape[0], flags, _stream(dev))
             if rc != -2:                      # VPTQ_ERR_UNSUPPORTED: these layers cannot share one launch
                 check(rc, "vptq_b200_quant_gemv_multi")
                 return
