@@ -161,3 +161,55 @@ def test_c_abi_host_builder_is_byte_identical(c):
     assert np.array_equal(out, stream.numpy().reshape(-1))
     # too small a buffer is refused, not overrun
     assert lib.vptq_b200_sliced_build_host(*args, out.ctypes.data, 16, offs_c.ctypes.data, ctypes.byref(steps)) == -3
+
+
+def test_builders_agree_on_random_shapes():
+    """Fuzz: tensor builder == C host builder, and the lists still evaluate to the oracle's sums."""
+    import ctypes
+    from vptq_b200 import native
+    lib = native.lib()
+    rng = np.random.default_rng(2024)
+    for trial in range(12):
+        K = int(rng.choice([16384, 32768, 65536]))
+        Kr = int(rng.choice([-1, 2, 64, 256]))
+        I = int(rng.integers(33, 700))
+        O = int(rng.integers(1, 90))
+        L = vo.make_layer(I, O, vector_len=8, num_centroids=K, num_res_centroids=Kr, dtype="fp16", seed=100 + trial)
+        ind_t = torch.from_numpy(np.ascontiguousarray(L.indices))
+        stream, offs = sliced.build_sliced(ind_t, num_centroids=K, num_res_centroids=Kr, group_size=I, out_features=O)
+        ind = np.ascontiguousarray(L.indices[0])
+        Ro, NS = (O + 7) // 8, K // 8192
+        offs_c = np.zeros(NS * Ro + 1, dtype=np.uint32)
+        steps = ctypes.c_size_t(0)
+        out = np.zeros(max(stream.numel(), 1), dtype=np.uint8)
+        rc = lib.vptq_b200_sliced_build_host(ind.ctypes.data, ind.shape[1], O, I, K, Kr, out.ctypes.data, out.size,
+                                             offs_c.ctypes.data, ctypes.byref(steps))
+        assert rc == 0, native.last_error()
+        assert steps.value == stream.shape[0]
+        assert np.array_equal(offs_c.astype(np.int64), offs.numpy().astype(np.int64)), (K, Kr, I, O)
+        assert np.array_equal(out[:stream.numel()], stream.numpy().reshape(-1)), (K, Kr, I, O)
+        # value check through the float64 evaluator
+        x = vo.make_x(1, I, "fp16", seed=trial)
+        xf = vo.to_f32(x, "fp16").astype(np.float64).reshape(-1)
+        perm = np.asarray(L.perm).astype(np.uint16).astype(np.int64)
+        sc, wb = vo.to_f32(L.weight_scale, "fp16").astype(np.float64), vo.to_f32(L.weight_bias, "fp16").astype(np.float64)
+        y = sliced.emulate(stream, offs, num_centroids=K, num_res_centroids=Kr, group_size=I, out_features=O,
+                           centroids=torch.from_numpy(vo.to_f32(L.centroids, "fp16")),
+                           res_centroids=None if Kr <= 0 else torch.from_numpy(vo.to_f32(L.res_centroids, "fp16")),
+                           xq=torch.from_numpy(xf[perm] * sc[perm])).numpy()[:O] + float((xf * wb).sum())
+        y_star = vo.quant_gemm(x, L).astype(np.float64).reshape(-1)
+        assert np.max(np.abs(y - y_star)) <= 1e-5 * max(1.0, np.max(np.abs(y_star))), (K, Kr, I, O)
+
+
+def test_host_builder_rejects_what_the_kernel_does_not_cover():
+    import ctypes
+    from vptq_b200 import native
+    lib = native.lib()
+    ind = np.zeros((4, 64), dtype=np.int32)
+    offs = np.zeros(64, dtype=np.uint32)
+    steps = ctypes.c_size_t(0)
+    for K, Kr in ((8192, 256), (4096, -1), (65536, 512), (24576, 16)):
+        rc = lib.vptq_b200_sliced_build_host(ind.ctypes.data, 64, 32, 64, K, Kr, None, 0, offs.ctypes.data, ctypes.byref(steps))
+        assert rc in (-1, -2), (K, Kr)
+    assert lib.vptq_b200_sliced_build_host(ind.ctypes.data, 1, 32, 64, 65536, 256, None, 0, offs.ctypes.data,
+                                           ctypes.byref(steps)) == -1      # stride shorter than a packed row
