@@ -126,7 +126,7 @@ def build_stack(m, q, device, rank, world, dtype):
                 num_codebooks=1, group_size=i, outlier_size=0, outlier_vector_len=-1, num_outlier_centroids=-1,
                 indices=t["indices"], centroids=t["centroids"], res_centroids=t["res_centroids"], outlier_indices=None,
                 outlier_centroids=None, perm=t["perm"], weight_scale=t["weight_scale"], weight_bias=t["weight_bias"],
-                bias=None, sliced=None if world == 1 else False)   # tensor-parallel launches use the generic kernel
+                bias=None, lists=None if world == 1 else False)   # tensor-parallel launches use the generic kernel
             if os.environ.get("BENCH_DEBUG"):
                 pv = t["perm"].view(torch.uint16).to(torch.int64)
                 assert int(pv.max()) == i - 1 and int(pv.min()) == 0 and pv.unique().numel() == i, "bad perm"
@@ -395,9 +395,9 @@ def run_ours(args):
         abytes = algorithmic_bytes(m, q, 1, world)         # per rank and step
         achieved = abytes / (ms_step * 1e-3) / 1e9
         traffic = None
-        # single-GPU decode runs the sliced-codebook kernel (tensor-parallel launches use the generic one)
-        sliced_on = world == 1 and os.environ.get("VPTQ_B200_SLICED", native.SLICED_DEFAULT) != "0" and \
-            "sliced=0" not in os.environ.get("VPTQ_B200_GEMV_TUNE", "")
+        # single-GPU decode runs the list-based kernel (tensor-parallel launches use the generic one)
+        sliced_on = world == 1 and os.environ.get("VPTQ_B200_LISTS", native.LISTS_DEFAULT) != "0" and \
+            "lists=0" not in os.environ.get("VPTQ_B200_GEMV_TUNE", "")
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "gemv_traffic.json")))
             traffic = (tj["sliced"] if sliced_on else tj)["dram_bytes_per_token"] // (n_launch * world)
@@ -425,8 +425,8 @@ def run_ours(args):
                     "wall_ms_per_step": round(wall_e2e / e2e_steps, 4)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
-                         "kernel": ("gemv_sliced_kernel<half,true> (csrc/gemv_sliced.cu: 128 KiB codebook slice per SM, "
-                                    "shared-memory gathers)") if sliced_on else
+                         "kernel": ("gemv_lists_kernel<half,true> (csrc/gemv_lists.cu: 64 KiB codebook slices in shared "
+                                    "memory, slice x tile index lists)") if sliced_on else
                                    "gemv_body<half,8,1,false,true> (entry points gemv_kernel / gemv_multi_kernel)",
                          "algorithmic_bytes_per_launch": abytes // n_launch,
                          "avg_launch_us": round(ms_step * 1e3 / n_launch, 3),

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define VPTQ_B200_ABI_VERSION 4
+#define VPTQ_B200_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define VPTQ_B200_API __attribute__((visibility("default")))
@@ -117,23 +117,29 @@ typedef struct vptq_linear_desc {
   const void* weight_scale_q; /* [I] or NULL */
   const void* weight_bias_q;  /* [I] or NULL */
 
-  /* Optional second load-time derivative: the SAME indices re-bucketed for the decode kernel that
-     keeps a 128 KiB slice of a large main codebook in each SM's shared memory (NULL = not provided:
-     the packed words above are decoded directly; results agree up to fp32 summation order).
-     Eligible layers: vector_len 8, one codebook group, no outlier columns, K a multiple of 8192
-     (NS = K / 8192 slices, 2 <= NS <= 8), Kr <= 256; used for single-token calls.
-     For slice s and index row r, list (s, r) holds the fields of row r whose main index lies in
-     [8192 s, 8192 (s+1)), in any order (the builder orders them so that 8 consecutive entries hit 8
-     different 16-byte bank groups), padded with null entries to whole steps of 32 entries.  Lists
-     are stored slice-major, one step record after the other:
-       sliced_offsets[s*Ro + r]  first step of list (s, r); sliced_offsets[NS*Ro] = number of steps
-       sliced_stream             per step: 32 little-endian words  (main index & 8191) | column << 16
-                                 (null entry: column = in_features, an x' slot the kernel keeps at 0),
-                                 then -- only when Kr > 0 -- 32 bytes, the residual indices of the
-                                 same 32 fields: 160 (128) bytes per step, 16-byte aligned.
-     vptq_b200.native.make_desc(sliced=True) builds both. */
-  const void* sliced_stream;
-  const uint32_t* sliced_offsets;
+  /* Optional second load-time derivative: the SAME indices re-bucketed into slice x tile lists for the
+     decode kernel that keeps 64 KiB slices of a large main codebook in each SM's shared memory
+     (NULL = not provided: the packed words above are decoded directly; results agree up to fp32
+     summation order and one fp16 rounding of c + r, which is what the reference's kernel does too).
+     Eligible layers: vector_len 8, one codebook group, no outlier columns, K = NS * 4096 with
+     2 <= NS <= 16, Kr <= 256; used for single-token calls.  Geometry:
+       NT  = ceil(I / 4096) column tiles over the ORIGINAL input features,
+       TCW = lists_tile_cols = ceil(ceil(I / NT) / 8) * 8 features per tile,
+       combo = tile * NS + slice,  unit u = combo * Ro + r  (U = NS * NT * Ro units).
+     Unit u lists the fields of index row r whose main index lies in [4096 s, 4096 (s+1)) and whose
+     original feature perm[c] lies in [TCW t, TCW (t+1)), in any order (the builders order them so
+     that 8 consecutive entries hit 8 different 16-byte bank groups), as 32-bit entries
+       (main index & 4095) | (perm[c] - TCW t) << 12 | residual index << 24,
+     padded with zero words to whole steps of 32 entries; every unit has at least one step.
+       lists_stream  uint32 [T][32], units in increasing u, 16-byte aligned
+       lists_tab     uint32 [U + 1]: tab[u] = first step of unit u | (number of valid entries in the
+                     unit's LAST step, 0..32) << 26;  tab[U] = T
+     vptq_b200.native.make_desc(lists=True) (GPU, torch) and vptq_b200_lists_build_host (CPU) build
+     them; perm is folded in, so the kernel never reads `perm`. */
+  const uint32_t* lists_stream;
+  const uint32_t* lists_tab;
+  int32_t lists_tile_cols;
+  int32_t lists_reserved;
 } vptq_linear_desc;
 
 typedef enum vptq_op {
@@ -166,18 +172,19 @@ VPTQ_B200_API int vptq_b200_quant_gemv(const vptq_linear_desc* desc, const void*
                          size_t workspace_bytes, uint32_t flags, void* stream);
 
 /*
- * Host-side builder of the sliced index lists of ONE layer (vptq_linear_desc::sliced_stream /
- * ::sliced_offsets) for hosts that do not use vptq_b200.native: plain CPU code, no GPU work.  Reads
- * the packed index words [Ro][index_stride_row] of a one-codebook layer from HOST memory and writes
- * HOST buffers the caller uploads (16-byte aligned on the device).  offsets_out must hold
- * (K / 8192) * ceil(O / 8) + 1 words.  With stream_out == NULL only offsets_out and *steps_out are
- * produced (sizing call: stream bytes = *steps_out * (Kr > 0 ? 160 : 128)).  Byte-identical to the
- * lists vptq_b200.sliced.build_sliced produces on the GPU.
+ * Host-side builder of the slice x tile lists of ONE layer (vptq_linear_desc::lists_stream / ::lists_tab)
+ * for hosts that do not use vptq_b200.native: plain CPU code, no GPU work.  Reads the packed index
+ * words [Ro][index_stride_row] of a one-codebook layer and its perm (uint16 [I], NULL = identity) from
+ * HOST memory and writes HOST buffers the caller uploads (stream 16-byte aligned on the device).
+ * tab_out must hold (K / 4096) * ceil(I / tile_cols) * ceil(O / 8) + 1 words; *tile_cols_out receives
+ * lists_tile_cols.  With stream_out == NULL only tab_out, *steps_out and *tile_cols_out are produced
+ * (sizing call: stream bytes = *steps_out * 128).  Byte-identical to vptq_b200.lists.build_lists.
  */
-VPTQ_B200_API int vptq_b200_sliced_build_host(const int32_t* indices_host, int64_t index_stride_row,
-                                              int32_t out_features, int32_t group_size, int32_t num_centroids,
-                                              int32_t num_res_centroids, void* stream_out, size_t stream_capacity,
-                                              uint32_t* offsets_out, size_t* steps_out);
+VPTQ_B200_API int vptq_b200_lists_build_host(const int32_t* indices_host, int64_t index_stride_row,
+                                             int32_t out_features, int32_t in_features, int32_t num_centroids,
+                                             int32_t num_res_centroids, const uint16_t* perm_host,
+                                             void* stream_out, size_t stream_capacity, uint32_t* tab_out,
+                                             size_t* steps_out, int32_t* tile_cols_out);
 
 /*
  * Decode path, horizontally fused: up to 4 layers that read the SAME x (q/k/v, gate/up of a
@@ -191,8 +198,9 @@ VPTQ_B200_API int vptq_b200_quant_gemv_multi(int32_t n, const vptq_linear_desc* 
                                              int32_t tokens, uint32_t flags, void* stream);
 
 /* Same, with a workspace (first 256 KiB zero at rest, size >= the sum of vptq_b200_workspace_bytes(desc_l,
- * tokens, VPTQ_OP_GEMV) over the layers): lets the library pick kernel variants that reduce through
- * global memory.  Results are identical to vptq_b200_quant_gemv_multi. */
+ * tokens, VPTQ_OP_GEMV) over the layers).  Needed for the list-based decode kernel (layers carrying
+ * lists_stream reduce their per-combo partial sums through it); without a workspace such layers run the
+ * generic kernel.  Same results up to fp32 summation order. */
 VPTQ_B200_API int vptq_b200_quant_gemv_multi_ws(int32_t n, const vptq_linear_desc* const* descs, const void* x,
                                                 int64_t x_stride, void* const* ys, const int64_t* y_strides,
                                                 int32_t tokens, void* workspace, size_t workspace_bytes,
@@ -236,9 +244,10 @@ VPTQ_B200_API int vptq_b200_dequant(const vptq_linear_desc* desc, void* w_out, v
                       size_t workspace_bytes, void* stream);
 
 /*
- * Prefill path: y = x W^T + bias for many tokens; weight tiles are dequantised on chip and fed
- * to tcgen05 tensor-core MMAs (replaces dequant + torch F.linear,
- * vptq/ops/quant_gemm.py:231-275).
+ * Prefill path: y = x W^T + bias for many tokens (replaces dequant + torch F.linear,
+ * vptq/ops/quant_gemm.py:231-275): the quantised weight is dequantised once into the workspace (16-bit,
+ * quantised column order, scale / bias / perm kept out of it) and fed by TMA to a tcgen05 tensor-core
+ * GEMM with TMEM accumulators.
  */
 VPTQ_B200_API int vptq_b200_quant_gemm(const vptq_linear_desc* desc, const void* x, int64_t x_stride, void* y,
                          int64_t y_stride, int32_t tokens, void* workspace,

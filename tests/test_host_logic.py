@@ -147,9 +147,10 @@ def test_c_abi_exports_every_declared_symbol():
 
 def test_c_abi_struct_layout_matches_header():
     from vptq_b200 import native
-    # 2 + 10 int32 (48 B) then 17 pointer/int64 slots
-    assert ctypes.sizeof(native.LinearDesc) == 48 + 17 * 8
+    # 2 + 10 int32 (48 B), 17 pointer/int64 slots, then lists_tile_cols + one reserved int32
+    assert ctypes.sizeof(native.LinearDesc) == 48 + 17 * 8 + 8
     assert native.LinearDesc.indices.offset == 48
+    assert native.LinearDesc.lists_tab.offset == 48 + 16 * 8 and native.LinearDesc.lists_tile_cols.offset == 48 + 17 * 8
 
 
 def _desc(**over):
@@ -173,6 +174,9 @@ def test_c_abi_validation_and_workspace_without_gpu():
     # fixed 256 KiB zero-at-rest counter region; this layer reduces its column chunks through a
     # thread-block cluster, so no global partial-sum scratch (B200 geometry assumed without a GPU)
     assert ws == 65536 * 4
+    # with slice x tile lists the per-combo partial sums go through the workspace: Q * Ro * 32 bytes behind it
+    with_lists = _desc(lists_stream=0x40000, lists_tab=0x50000, lists_tile_cols=4096)
+    assert L.vptq_b200_workspace_bytes(ctypes.byref(with_lists), 1, native.OP_GEMV) == 65536 * 4 + 16 * 512 * 32
     # 16 codebook groups -> more than 8 chunks -> global-memory split-K scratch behind the counters
     many = _desc(num_codebooks=16, group_size=256, index_stride_row=192, index_stride_codebook=512 * 192)
     assert L.vptq_b200_workspace_bytes(ctypes.byref(many), 1, native.OP_GEMV) == 65536 * 4 + 16 * 4096 * 4

@@ -168,7 +168,7 @@ size_t vptq_b200_workspace_bytes(const vptq_linear_desc* desc, int32_t tokens, i
       const DeviceInfo* dev = device_info();
       GemvPlan pl;
       if (gemv_make_plan(*desc, tokens, dev ? *dev : b200, &pl)) return 0;
-      return std::max(pl.ws_counters_bytes + pl.ws_partials_bytes, gemv_sliced_workspace_bytes(*desc));
+      return std::max(pl.ws_counters_bytes + pl.ws_partials_bytes, gemv_lists_workspace_bytes(*desc));
     }
     case VPTQ_OP_DEQUANT: return dequant_workspace_bytes(*desc);
     case VPTQ_OP_GEMM: return gemm_workspace_bytes(*desc, tokens);

@@ -24,9 +24,9 @@ std::mutex g_mutex;
 std::unordered_set<const void*> g_attr_done;
 std::map<std::tuple<const void*, int, int, int>, int> g_max_clusters;
 
-// Developer tuning knobs (not part of the ABI): VPTQ_B200_GEMV_TUNE="rep=1,stages=2,seg=512,warps=16,cpg=4,wsplit=2,cluster=0,sliced=0"
+// Developer tuning knobs (not part of the ABI): VPTQ_B200_GEMV_TUNE="rep=1,stages=2,seg=512,warps=16,cpg=4,wsplit=2,cluster=0,lists=0"
 struct Tune {
-  int rep = -1, stages = 0, seg = 0, warps = 0, cpg = 0, cluster = -1, wsplit = 0, sliced = -1;
+  int rep = -1, stages = 0, seg = 0, warps = 0, cpg = 0, cluster = -1, wsplit = 0, lists = -1;
 };
 const Tune& tune() {
   static Tune t = [] {
@@ -38,7 +38,7 @@ const Tune& tune() {
       if (p) dst = std::atoi(p + std::strlen(key));
     };
     get("rep=", r.rep), get("stages=", r.stages), get("seg=", r.seg), get("warps=", r.warps), get("cpg=", r.cpg),
-        get("cluster=", r.cluster), get("wsplit=", r.wsplit), get("sliced=", r.sliced);
+        get("cluster=", r.cluster), get("wsplit=", r.wsplit), get("lists=", r.lists);
     return r;
   }();
   return t;
@@ -90,7 +90,7 @@ int max_active_clusters(const void* fn, int csize, int threads, int smem, int op
   return n;
 }
 
-int gemv_tune_sliced() { return tune().sliced; }
+int gemv_tune_lists() { return tune().lists; }
 
 // developer aid: phase-stamp buffer (device pointer) handed to every subsequent GEMV launch
 static unsigned long long* g_prof_buffer = nullptr;
@@ -346,12 +346,12 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
     set_error("gemv: vector_len %d not supported (2,4,6,8,10,12,16)", d.vector_len);
     return VPTQ_ERR_UNSUPPORTED;
   }
-  // decode proper (one token) of a layer that carries sliced index lists: shared-memory gathers
-  if (tokens == 1 && gemv_tune_sliced() != 0 && gemv_sliced_eligible(d)) {
+  // decode proper (one token) of a layer that carries slice x tile lists: shared-memory gathers
+  if (tokens == 1 && gemv_tune_lists() != 0 && gemv_lists_eligible(d)) {
     const vptq_linear_desc* dp = &d;
     void* yp = y;
-    const int rc = gemv_sliced_launch(1, &dp, x, &yp, flags, stream, workspace, workspace_bytes);
-    if (rc != VPTQ_ERR_UNSUPPORTED) return rc;
+    const int rc = gemv_lists_launch(1, &dp, x, &yp, flags, stream, workspace, workspace_bytes);
+    if (rc != VPTQ_ERR_UNSUPPORTED && rc != VPTQ_ERR_WORKSPACE) return rc;
   }
   GemvPlan pl;
   if (int rc = gemv_make_plan(d, tokens, *dev, &pl)) return rc;
@@ -395,12 +395,12 @@ int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x
     set_error("gemv_multi: 1..%d layers and 1..2 tokens (got %d layers, %d tokens)", kMaxFused, n, tokens);
     return VPTQ_ERR_UNSUPPORTED;
   }
-  if (tokens == 1 && !(tp && tp->world > 1) && gemv_tune_sliced() != 0) {
+  if (tokens == 1 && !(tp && tp->world > 1) && gemv_tune_lists() != 0 && workspace) {
     bool all = true;
-    for (int l = 0; l < n; ++l) all = all && gemv_sliced_eligible(*descs[l]);
+    for (int l = 0; l < n; ++l) all = all && gemv_lists_eligible(*descs[l]);
     if (all) {
-      const int rc = gemv_sliced_launch(n, descs, x, ys, flags, stream, workspace, workspace_bytes);
-      if (rc != VPTQ_ERR_UNSUPPORTED) return rc;
+      const int rc = gemv_lists_launch(n, descs, x, ys, flags, stream, workspace, workspace_bytes);
+      if (rc != VPTQ_ERR_UNSUPPORTED && rc != VPTQ_ERR_WORKSPACE) return rc;
     }
   }
   const vptq_linear_desc& d0 = *descs[0];

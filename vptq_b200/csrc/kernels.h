@@ -85,21 +85,20 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
 int ensure_smem_attr(const void* fn, int bytes);  // opt in to `bytes` of dynamic shared memory, once per kernel
 // how many clusters of `csize` CTAs (threads, smem each) the device can hold at once; <= 0: unknown
 int max_active_clusters(const void* fn, int csize, int threads, int smem, int optin);
-int gemv_tune_sliced();  // developer knob VPTQ_B200_GEMV_TUNE="sliced=0|1" (-1: not set)
+int gemv_tune_lists();  // developer knob VPTQ_B200_GEMV_TUNE="lists=0|1" (-1: not set)
 
 // -------------------------------------------------------------------------------------------
-// decode GEMV, sliced-codebook variant (gemv_sliced.cu): one token, layers carrying the re-bucketed
-// index lists of vptq_linear_desc::sliced_*.  A cluster of NS CTAs covers a range of index rows,
-// CTA s keeps slice s of the main codebook (128 KiB) in shared memory and walks list (s, r) of its
-// rows: every codebook gather is a shared-memory access instead of an L1/L2 one.
+// decode GEMV, list-based variant (gemv_lists.cu): one token, layers carrying the slice x tile lists of
+// vptq_linear_desc::lists_*.  Every CTA keeps one or two 64 KiB slices of the main codebook in shared
+// memory and walks the lists of its units: every codebook gather is a shared-memory access instead of an
+// L1/L2 one; the per-combo partial sums meet in the workspace (arrival counters, last arriver writes y).
 // -------------------------------------------------------------------------------------------
 constexpr int kMaxFusedLayers = 4;
-bool gemv_sliced_eligible(const vptq_linear_desc& d);
-// n layers reading the same x in one launch.  VPTQ_ERR_UNSUPPORTED: use the generic kernel.
-// `workspace` (optional): needed only by the experimental global-memory reduction (sliced=2 tuning knob)
-int gemv_sliced_launch(int n, const vptq_linear_desc* const* descs, const void* x, void* const* ys, uint32_t flags,
-                       cudaStream_t stream, void* workspace = nullptr, size_t workspace_bytes = 0);
-size_t gemv_sliced_workspace_bytes(const vptq_linear_desc& d);  // 0 when the layer is not eligible
+bool gemv_lists_eligible(const vptq_linear_desc& d);
+// n layers reading the same x in one launch.  VPTQ_ERR_UNSUPPORTED / VPTQ_ERR_WORKSPACE: use the generic kernel.
+int gemv_lists_launch(int n, const vptq_linear_desc* const* descs, const void* x, void* const* ys, uint32_t flags,
+                      cudaStream_t stream, void* workspace, size_t workspace_bytes);
+size_t gemv_lists_workspace_bytes(const vptq_linear_desc& d);  // 0 when the layer is not eligible
 
 // -------------------------------------------------------------------------------------------
 // dequant

@@ -157,13 +157,40 @@ class VQuantLinear(nn.Module):
             self._packed = (key, packed.contiguous())
         return self._packed[1]
 
+    def _cache_key(self, t, dtype, device):
+        # data_ptr catches .to() / re-assignment, _version catches in-place updates (load_state_dict, copy_)
+        return tuple((a.data_ptr(), a.dtype, a._version) if a is not None else None for a in t) + (dtype, device)
+
+    def prepare(self, dtype: Optional[torch.dtype] = None) -> "VQuantLinear":
+        """Build the C-ABI descriptor and its load-time derivatives (scale/bias in quantised order, the
+        slice x tile index lists of the decode kernel) now instead of inside the first forward: call once
+        after loading the checkpoint, before capturing CUDA graphs."""
+        dtype = dtype or self.centroids.weight.dtype
+        x = torch.zeros(1, self.in_features, dtype=dtype, device=self.centroids.weight.device)
+        self.forward(x)
+        return self
+
+    def __getstate__(self):
+        # the cached descriptor holds raw pointers (ctypes): never pickled or deep-copied
+        st = self.__dict__.copy()
+        st["_desc_cache"], st["_desc_key"], st["_packed"] = [], None, None
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
+
     def forward(self, x, W=None, H=None):
         """x: [..., in_features] fp16/bf16 on the GPU -> [..., out_features]."""
         if self.enable_proxy_error:
             return self.proxy_error_forward(W, H)   # quantizer-side debugging aid
         t = self._tensors()
-        key = tuple((a.data_ptr(), a.dtype) if a is not None else None for a in t) + (x.dtype, x.device)
-        if key != self._desc_key:                    # parameters were moved / reloaded
+        key = self._cache_key(t, x.dtype, x.device)
+        if key != self._desc_key:                    # parameters were moved / reloaded / updated in place
             self._desc_cache = []
             self._desc_key = key
         indices, cent, resc, outi, outc, perm, ws, wb, bias = t

@@ -14,7 +14,7 @@ from typing import Optional
 
 import torch
 
-from . import sliced as _sliced
+from . import lists as _lists
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvptq_b200.so")
@@ -22,14 +22,14 @@ LIB_PATH = os.path.join(_HERE, "libvptq_b200.so")
 VPTQ_FP16, VPTQ_BF16 = 0, 1
 OP_GEMV, OP_DEQUANT, OP_GEMM, OP_GEMV_V2 = 0, 1, 2, 3
 FLAG_PDL = 1
-ABI_VERSION = 4
-SLICED_DEFAULT = "1"   # VPTQ_B200_SLICED when unset
+ABI_VERSION = 5
+LISTS_DEFAULT = "1"   # VPTQ_B200_LISTS when unset
 
 EXPORTS = (
     "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
     "vptq_b200_dequant", "vptq_b200_quant_gemm", "vptq_b200_quant_gemv_v2", "vptq_b200_linear_host",
     "vptq_b200_debug_phase_stamps", "vptq_b200_quant_gemv_multi", "vptq_b200_quant_gemv_multi_tp",
-    "vptq_b200_sliced_build_host", "vptq_b200_quant_gemv_multi_ws",
+    "vptq_b200_lists_build_host", "vptq_b200_quant_gemv_multi_ws",
 )
 
 MAX_FUSED, MAX_RANKS = 4, 8
@@ -61,7 +61,8 @@ class LinearDesc(ctypes.Structure):
         ("outlier_indices", ctypes.c_void_p), ("outlier_centroids", ctypes.c_void_p),
         ("perm", ctypes.c_void_p), ("weight_scale", ctypes.c_void_p), ("weight_bias", ctypes.c_void_p),
         ("bias", ctypes.c_void_p), ("weight_scale_q", ctypes.c_void_p), ("weight_bias_q", ctypes.c_void_p),
-        ("sliced_stream", ctypes.c_void_p), ("sliced_offsets", ctypes.c_void_p),
+        ("lists_stream", ctypes.c_void_p), ("lists_tab", ctypes.c_void_p),
+        ("lists_tile_cols", ctypes.c_int32), ("lists_reserved", ctypes.c_int32),
     ]
 
 
@@ -103,8 +104,9 @@ def lib() -> ctypes.CDLL:
         L.vptq_b200_quant_gemv_multi_tp.argtypes = [i32, ctypes.POINTER(dp), vp, i64, ctypes.POINTER(vp),
                                                     ctypes.POINTER(i64), i32, ctypes.POINTER(TpExchange), u32, vp]
         L.vptq_b200_quant_gemv_multi_tp.restype = ctypes.c_int
-        L.vptq_b200_sliced_build_host.argtypes = [vp, i64, i32, i32, i32, i32, vp, sz, vp, ctypes.POINTER(sz)]
-        L.vptq_b200_sliced_build_host.restype = ctypes.c_int
+        L.vptq_b200_lists_build_host.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp, sz, vp, ctypes.POINTER(sz),
+                                                 ctypes.POINTER(i32)]
+        L.vptq_b200_lists_build_host.restype = ctypes.c_int
         L.vptq_b200_debug_phase_stamps.argtypes = [vp]
         L.vptq_b200_debug_phase_stamps.restype = None
         for f in ("vptq_b200_quant_gemv", "vptq_b200_quant_gemm", "vptq_b200_dequant", "vptq_b200_quant_gemv_v2",
@@ -154,17 +156,17 @@ def make_desc(*, dtype: torch.dtype, in_features: int, out_features: int, vector
               outlier_indices: Optional[torch.Tensor], outlier_centroids: Optional[torch.Tensor],
               perm: Optional[torch.Tensor], weight_scale: Optional[torch.Tensor],
               weight_bias: Optional[torch.Tensor], bias: Optional[torch.Tensor],
-              derive: bool = True, sliced: Optional[bool] = None) -> LinearDesc:
+              derive: bool = True, lists: Optional[bool] = None) -> LinearDesc:
     """Describe one layer's tensors for the C ABI.  Tensors are borrowed: keep them alive.
 
     With `derive` (default) the load-time derivatives the ABI accepts are built here, once:
     weight_scale / weight_bias in quantised column order (`t[perm]`).  They hang off the returned
     descriptor (`desc._keep`) so they live as long as it does.
 
-    `sliced`: also build the slice-bucketed index lists (vptq_b200.sliced) that let single-token calls
-    of large-codebook layers gather from shared memory; costs 5 bytes per index on top of the packed
-    words.  None = the VPTQ_B200_SLICED environment variable (default on); ignored for layers the
-    sliced kernel does not cover.
+    `lists`: also build the slice x tile index lists (vptq_b200.lists) that let single-token calls of
+    large-codebook layers gather from shared memory; costs 4 bytes per index (+ ~6 % padding) on top
+    of the packed words (3 bytes per index for the 65536+256 configuration).  None = the
+    VPTQ_B200_LISTS environment variable (default on); ignored for layers the list kernel does not cover.
     """
     if indices.dtype != torch.int32:
         raise RuntimeError("`indices` must be packed int32 words (is_indice_packed=True); "
@@ -203,16 +205,17 @@ def make_desc(*, dtype: torch.dtype, in_features: int, out_features: int, vector
         ws_q, wb_q = weight_scale[pidx].contiguous(), weight_bias[pidx].contiguous()
         d.weight_scale_q, d.weight_bias_q = ws_q.data_ptr(), wb_q.data_ptr()
         d._keep = (ws_q, wb_q)
-    if sliced is None:
-        sliced = os.environ.get("VPTQ_B200_SLICED", SLICED_DEFAULT) != "0"
-    if sliced and derive and _sliced.eligible(
+    if lists is None:
+        lists = os.environ.get("VPTQ_B200_LISTS", LISTS_DEFAULT) != "0"
+    if lists and derive and _lists.eligible(
             vector_len=d.vector_len, num_centroids=d.num_centroids, num_res_centroids=d.num_res_centroids,
-            num_codebooks=d.num_codebooks, outlier_size=d.outlier_size, in_features=d.in_features):
-        stream, offs = _sliced.build_sliced(indices, num_centroids=d.num_centroids,
-                                            num_res_centroids=d.num_res_centroids, group_size=d.group_size,
-                                            out_features=d.out_features)
-        d.sliced_stream, d.sliced_offsets = stream.data_ptr(), offs.data_ptr()
-        d._keep = d._keep + (stream, offs)
+            num_codebooks=d.num_codebooks, outlier_size=d.outlier_size, in_features=d.in_features) and (
+            weight_scale is None or (weight_scale.data_ptr() % 16 == 0 and weight_bias.data_ptr() % 16 == 0)):
+        stream, tab, tcw = _lists.build_lists(indices, num_centroids=d.num_centroids,
+                                              num_res_centroids=d.num_res_centroids, in_features=d.in_features,
+                                              out_features=d.out_features, perm=perm)
+        d.lists_stream, d.lists_tab, d.lists_tile_cols = stream.data_ptr(), tab.data_ptr(), int(tcw)
+        d._keep = d._keep + (stream, tab)
     return d
 
 
@@ -262,20 +265,18 @@ class FusedGemv:
         self.y_arr = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
         self.stride_arr = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
         self.separate = False
-        self.with_workspace = "sliced=2" in os.environ.get("VPTQ_B200_GEMV_TUNE", "")
+        self.ws_bytes = None
 
     def __call__(self, x2d: torch.Tensor, flags: int = 0) -> None:
         dev = x2d.device
         if not self.separate:
             with torch.cuda.device(dev):
-                if self.with_workspace:   # experimental kernel variants that reduce through global memory
-                    ws = workspace(dev, sum(workspace_bytes(d, x2d.shape[0], OP_GEMV) for d in self.descs))
-                    rc = lib().vptq_b200_quant_gemv_multi_ws(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0),
-                                                             self.y_arr, self.stride_arr, x2d.shape[0], ws.data_ptr(),
-                                                             ws.numel(), flags, _stream(dev))
-                else:
-                    rc = lib().vptq_b200_quant_gemv_multi(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0),
-                                                          self.y_arr, self.stride_arr, x2d.shape[0], flags, _stream(dev))
+                if self.ws_bytes is None:
+                    self.ws_bytes = sum(workspace_bytes(d, x2d.shape[0], OP_GEMV) for d in self.descs)
+                ws = workspace(dev, self.ws_bytes)   # the list kernel reduces its partial sums through it
+                rc = lib().vptq_b200_quant_gemv_multi_ws(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0),
+                                                         self.y_arr, self.stride_arr, x2d.shape[0], ws.data_ptr(),
+                                                         ws.numel(), flags, _stream(dev))
             if rc != -2:                      # VPTQ_ERR_UNSUPPORTED: these layers cannot share one launch
                 check(rc, "vptq_b200_quant_gemv_multi")
                 return

@@ -23,7 +23,8 @@ __all__ = ["dequant", "quant_gemm", "quant_gemv_v2"]
 
 def _desc(*, dtype, indices, centroids, outlier_indices, outlier_centroids, residual_centroids, perm,
           weight_scale, weight_bias, bias, vector_len, outlier_vector_len, num_codebooks, num_centroids,
-          num_outlier_centroids, num_res_centroids, group_size, outlier_size, in_features, out_features):
+          num_outlier_centroids, num_res_centroids, group_size, outlier_size, in_features, out_features,
+          derive=True, lists=None):
     if perm is not None and perm.dtype not in (torch.int16, torch.uint16):
         # unpacked checkpoints keep perm as int64 (vqlinear.py:191-196)
         perm = perm.to(torch.int64).to(torch.uint16).contiguous()
@@ -34,7 +35,7 @@ def _desc(*, dtype, indices, centroids, outlier_indices, outlier_centroids, resi
         outlier_vector_len=outlier_vector_len, num_outlier_centroids=num_outlier_centroids, indices=indices,
         centroids=centroids, res_centroids=residual_centroids, outlier_indices=outlier_indices,
         outlier_centroids=outlier_centroids, perm=perm, weight_scale=weight_scale, weight_bias=weight_bias,
-        bias=bias), perm
+        bias=bias, derive=derive, lists=lists), perm
 
 
 def dequant(
@@ -83,7 +84,7 @@ def dequant(
         bias=None, vector_len=vector_len, outlier_vector_len=outlier_vector_len, num_codebooks=num_codebooks,
         num_centroids=num_centroids, num_outlier_centroids=num_outlier_centroids,
         num_res_centroids=num_res_centroids, group_size=group_size, outlier_size=outlier_size,
-        in_features=in_features, out_features=out_features)
+        in_features=in_features, out_features=out_features, derive=False, lists=False)
     w = torch.empty(out_features, in_features, dtype=centroids.dtype, device=centroids.device)
     native.dequant(desc, w)
     return w
@@ -138,7 +139,10 @@ def quant_gemm(
             weight_scale=weight_scale, weight_bias=weight_bias, bias=bias, vector_len=vector_len,
             outlier_vector_len=outlier_vector_len, num_codebooks=num_codebooks, num_centroids=num_centroids,
             num_outlier_centroids=num_outlier_centroids, num_res_centroids=num_res_centroids,
-            group_size=group_size, outlier_size=outlier_size, in_features=in_features, out_features=out_features)
+            group_size=group_size, outlier_size=outlier_size, in_features=in_features, out_features=out_features,
+            # a one-off descriptor (reference-style direct call) must not pay for re-bucketing the whole layer:
+            # the slice x tile lists are built only when the caller keeps the descriptor (VQuantLinear does)
+            lists=None if _desc_cache is not None else False)
         if _desc_cache is not None:
             _desc_cache.extend([desc, perm_])   # keep the converted perm alive with the descriptor
     x2d = x.reshape(-1, in_features)
