@@ -197,7 +197,7 @@ VPTQ_B200_API int vptq_b200_quant_gemv_multi(int32_t n, const vptq_linear_desc* 
                                              int64_t x_stride, void* const* ys, const int64_t* y_strides,
                                              int32_t tokens, uint32_t flags, void* stream);
 
-/* Same, with a workspace (first 256 KiB zero at rest, size >= the sum of vptq_b200_workspace_bytes(desc_l,
+/* Same, with a workspace (zero-initialised once, size >= the sum of vptq_b200_workspace_bytes(desc_l,
  * tokens, VPTQ_OP_GEMV) over the layers).  Needed for the list-based decode kernel (layers carrying
  * lists_stream reduce their per-combo partial sums through it); without a workspace such layers run the
  * generic kernel.  Same results up to fp32 summation order. */

@@ -171,15 +171,17 @@ def test_c_abi_validation_and_workspace_without_gpu():
     from vptq_b200 import native
     L = native.lib()
     ws = L.vptq_b200_workspace_bytes(ctypes.byref(_desc()), 1, native.OP_GEMV)
-    # fixed 256 KiB zero-at-rest counter region; this layer reduces its column chunks through a
-    # thread-block cluster, so no global partial-sum scratch (B200 geometry assumed without a GPU)
-    assert ws == 65536 * 4
-    # with slice x tile lists the per-combo partial sums go through the workspace: Q * Ro * 32 bytes behind it
+    # fixed zero-at-rest head (256 KiB of counters + 4 MiB of 64-bit accumulators); this layer reduces its
+    # column chunks through a thread-block cluster, so no global partial-sum scratch behind it (B200
+    # geometry assumed without a GPU)
+    ZERO = 65536 * 4 + 65536 * 64
+    assert ws == ZERO
+    # with slice x tile lists the combos meet in the 64-bit fixed-point accumulators of that head
     with_lists = _desc(lists_stream=0x40000, lists_tab=0x50000, lists_tile_cols=4096)
-    assert L.vptq_b200_workspace_bytes(ctypes.byref(with_lists), 1, native.OP_GEMV) == 65536 * 4 + 16 * 512 * 32
+    assert L.vptq_b200_workspace_bytes(ctypes.byref(with_lists), 1, native.OP_GEMV) == ZERO
     # 16 codebook groups -> more than 8 chunks -> global-memory split-K scratch behind the counters
     many = _desc(num_codebooks=16, group_size=256, index_stride_row=192, index_stride_codebook=512 * 192)
-    assert L.vptq_b200_workspace_bytes(ctypes.byref(many), 1, native.OP_GEMV) == 65536 * 4 + 16 * 4096 * 4
+    assert L.vptq_b200_workspace_bytes(ctypes.byref(many), 1, native.OP_GEMV) == ZERO + 16 * 4096 * 4
     for bad, msg in ((dict(vector_len=7), "vector_len"), (dict(num_centroids=1000), "power of two"),
                      (dict(group_size=4000), "in_features"), (dict(index_stride_row=100), "index_stride_row"),
                      (dict(res_centroids=0), "res_centroids"), (dict(dtype=3), "dtype"),

@@ -258,7 +258,7 @@ int launch_v(const DequantParams& p, int v, cudaStream_t stream) {
 
 size_t dequant_workspace_bytes(const vptq_linear_desc& d) {
   // the inverse permutation is scratch: it goes behind the zero-at-rest counter region
-  return d.perm ? kCounterRegionBytes + align_up(size_t(d.in_features) * 2, 256) : 0;
+  return d.perm ? kZeroRegionBytes + align_up(size_t(d.in_features) * 2, 256) : 0;
 }
 
 int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size_t workspace_bytes,
@@ -287,7 +287,7 @@ int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size
       set_error("dequant: workspace %zu bytes < required %zu (inverse permutation)", workspace_bytes, need);
       return VPTQ_ERR_WORKSPACE;
     }
-    uint16_t* inv = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(workspace) + kCounterRegionBytes);
+    uint16_t* inv = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(workspace) + kZeroRegionBytes);
     invert_perm_kernel<<<(d.in_features + 255) / 256, 256, 0, stream>>>(d.perm, inv, d.in_features);
     p.inv_perm = inv;
   }

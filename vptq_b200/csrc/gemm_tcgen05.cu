@@ -394,7 +394,7 @@ struct GemmWorkspace {
 GemmWorkspace gemm_layout(const vptq_linear_desc& d, int tokens) {
   GemmWorkspace w;
   w.kpad = int64_t(align_up(size_t(d.in_features), 64));  // whole BK blocks: no partially filled swizzle rows
-  size_t off = kCounterRegionBytes;                      // the zero-at-rest region stays untouched
+  size_t off = kZeroRegionBytes;                         // the zero-at-rest region stays untouched
   w.off_rowbias = off;
   off += align_up(size_t(tokens) * 4, 1024);
   w.off_xq = off;

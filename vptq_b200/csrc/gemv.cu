@@ -254,7 +254,7 @@ int gemv_make_plan(const vptq_linear_desc& d, int tokens, const DeviceInfo& dev,
       if (rows2 > rows_alloc) pl.cluster = 0;
     }
     pl.grid = pl.nch * pl.cpc;
-    pl.ws_counters_bytes = kCounterRegionBytes;
+    pl.ws_counters_bytes = kZeroRegionBytes;
     pl.ws_partials_bytes = (pl.nch > 1 && !pl.cluster) ? align_up(size_t(pl.nch) * pl.nt * Ro * v * 4, 256) : 0;
     *out = pl;
     return 0;

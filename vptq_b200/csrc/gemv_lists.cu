@@ -19,16 +19,21 @@
 //     entry a lane does LDS.32 (entry), LDS.128 (main), LDS.128 (residual), LDS.U16 (x'), then c + r in
 //     packed 16-bit arithmetic (exactly the reference's ADD2, csrc/kernels/quant_gemv.cuh:124-127) and 8
 //     mixed-precision FMAs into fp32 accumulators (fma.rn.f32.f16 -> SASS FHFMA);
-//   * a unit that lies inside one warp's run is reduced with 9 shuffles and its 8 sums go straight to the
-//     global partial table part[u][8]; the (at most two) units a run shares with its neighbours are parked
-//     in shared memory and merged in warp order;
-//   * reduction over the combos: row blocks of 32 index rows carry an arrival counter (units, not CTAs); the
-//     CTA whose arrival completes a block adds the Q = NS * NT partials of its rows in combo order
-//     (deterministic), adds bias and writes y.  No second kernel (the reference launches `sum(-1)`,
-//     csrc/quant_gemv.cu:235), no spinning on other CTAs, counters are left at zero.
+//   * a unit that lies inside one warp's run is reduced with 9 shuffles; the (at most two) units a run shares
+//     with its neighbours are parked in shared memory and merged in warp order;
+//   * reduction over the Q = NS * NT combos of a row: every unit adds its 8 sums, converted to 2^-30 fixed
+//     point, into a 64-bit accumulator row in the workspace with red.global.add.u64.  Integer addition is
+//     associative, so the result does not depend on the arrival order: bit-identical from run to run, like
+//     an ordered sum, without a partial-sum table (a last-arriver that adds Q partials per output was
+//     measured at 4-8 us of tail per launch).  Row blocks of 32 index rows carry an arrival counter (units,
+//     not CTAs); the CTA whose arrival completes a block converts its rows back, adds bias, writes y and
+//     zeroes the accumulators and the counter again.  No second kernel (the reference launches `sum(-1)`,
+//     csrc/quant_gemv.cu:235), no spinning on other CTAs.
 // Mathematics and reference citations: gemv_kernel.cuh (the reference's kernel is
 // csrc/kernels/quant_gemv.cuh:11-186; nothing of its structure is used here).
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <type_traits>
 
@@ -58,8 +63,8 @@ struct ListsLayer {
   const void* wbias;
   const void* bias;
   void* y;
-  float* part;         // [U][8] partial sums of this launch
-  uint32_t* counters;  // [ceil(Ro / kRB)], zero at rest
+  unsigned long long* yacc;  // [Ro][8] fixed-point (2^-30) accumulators, zero at rest
+  uint32_t* counters;        // [ceil(Ro / kRB)], zero at rest
   int I, O, Ro, Kr, NS, Q, TCW, U;
   int ncta;  // CTAs working on this layer
 };
@@ -84,6 +89,18 @@ __device__ __forceinline__ uint16_t lds_u16(uint32_t a) {
   uint16_t r;
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(r) : "r"(a));
   return r;
+}
+// a * b + c in one integer instruction (IMAD), so that mask -> scale -> add-base is two instructions, not three
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t r;
+  asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+  return r;
+}
+// fp32 -> 2^-30 fixed point (saturating) and back; |v| < 2^33 is far beyond any 16-bit activation
+constexpr float kFixScale = 1073741824.f, kFixInv = 1.f / 1073741824.f;
+__device__ __forceinline__ void red_add_fixed(unsigned long long* p, float v) {
+  const long long q = __float2ll_rn(v * kFixScale);
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(q) : "memory");
 }
 // sm_100 mixed-precision FMA (SASS FHFMA): fp16 x fp16 + fp32 -> fp32, the product is exact
 __device__ __forceinline__ float fma_f32_f16(uint16_t a, uint16_t b, float c) {
@@ -172,6 +189,7 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   const int cA = u0 / Ro, cB = (u1 - 1) / Ro;
   const bool two = cB != cA;
   const int nA = two ? cB * Ro - u0 : nun;  // units of segment A
+  const int rA0 = u0 - cA * Ro;             // its first index row (segment B starts at row 0)
   const int tA = cA / NS, sA = cA - tA * NS, tB = cB / NS, sB = cB - tB * NS;
   const bool xB_own = two && tB != tA;  // segment B reads another x' tile (then sB == 0)
 
@@ -273,6 +291,14 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
                    pol_stream);
     }
   };
+  // -------- x arrives from the previous kernel.  Its (coalesced) loads are issued first and complete while
+  // lane 0 of every warp queues the ring copies behind the slice copies in the TMA unit ---------------------
+  pdl_wait_prior_grid();
+  stamp(2);
+  const T* x = reinterpret_cast<const T*>(mp.x);
+  uint4 xa = make_uint4(0u, 0u, 0u, 0u), xb = xa;
+  if (colA) xa = load8<T>(x, fA, fAend, 0);
+  if (colB) xb = load8<T>(x, fB, fBend, 0);
   for (int qi = 0; qi < min(stages, nstage); ++qi) issue(qi, qi);
 
   // -------- residual codebook: copy k of entry i sits at 16-byte slot i*8 + k and lane L reads copy L mod 8,
@@ -284,17 +310,12 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
       for (int c = 0; c < kResRep; ++c) sts_v4(dst + uint32_t(c) * 16u, res_entry);
     }
   }
-  stamp(2);
-
-  // -------- x arrives from the previous kernel: x'[f] = x[f] * scale[f], coalesced ------------------------
-  pdl_wait_prior_grid();
   stamp(3);
+  // -------- x'[f] = x[f] * scale[f] -------------------------------------------------------------------------
   {
-    const T* x = reinterpret_cast<const T*>(mp.x);
     float bsA = 0.f, bsB = 0.f;
-    if (colA) sts_v4(s_x + uint32_t(j0) * 2u, make_xq<T>(load8<T>(x, fA, fAend, 0), scA, wbA, biasA, bsA));
-    if (colB)
-      sts_v4(s_x + 8192u + uint32_t(j0) * 2u, make_xq<T>(load8<T>(x, fB, fBend, 0), scB, wbB, biasB, bsB));
+    if (colA) sts_v4(s_x + uint32_t(j0) * 2u, make_xq<T>(xa, scA, wbA, biasA, bsA));
+    if (colB) sts_v4(s_x + 8192u + uint32_t(j0) * 2u, make_xq<T>(xb, scB, wbB, biasB, bsB));
     if (biasA) {  // (CTA-uniform conditions)
       const float v = warp_sum(bsA);
       if (lane == 0) s_red[warp] = v;
@@ -317,6 +338,7 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   // -------- main loop ---------------------------------------------------------------------------------
   if (nstage > 0) {
     const uint32_t res_lane = smem_u32(s_res) + uint32_t(lane & (kResRep - 1)) * 16u;
+    const uint32_t ring_lane = smem_u32(ring) + uint32_t(lane) * 4u;
     // the unit this run starts in: the last i with first(i) <= t_begin (every unit has >= 1 step)
     int u;
     {
@@ -341,7 +363,7 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
       const float mine = warp_reduce_to_lane<8>(acc, lane);
       const bool boundary = u == uF || !complete || u_end >= t_end;
       if (!boundary) {
-        if (lane < 8) L.part[size_t(u0 + u) * 8 + lane] = mine + cb;
+        if (lane < 8) red_add_fixed(L.yacc + size_t(u < nA ? rA0 + u : u - nA) * 8 + lane, mine + cb);
       } else {
         const int k = warp * 2 + (u == uF ? 0 : 1);
         if (lane < 8) s_piece[k * 8 + lane] = mine;
@@ -350,14 +372,25 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[e] = 0.f;
     };
-    int slot = 0;
+    auto advance = [&]() {
+      ++u;
+      if (u < nun) {
+        u_end = int(s_tab[u + 1] & kStepMask);
+        tail = s_tab[u] >> 26;
+      }
+    };
+    int slot = 0, qi = 0, t = 0;
     uint32_t par = 0;
     uint32_t slice_base = 0, x_base = 0;
-    int t = 0;
-    // one ring stage: FULL = all kSPS steps present
-    auto stage_body = [&](auto full_tag, int cnt) {
-      constexpr bool FULL = decltype(full_tag)::value;
-      const uint32_t st = smem_u32(ring + size_t(slot) * kStageBytes) + uint32_t(lane) * 4u;
+    // One ring stage = one batch of up to kSPS steps: all entry words, then all gathers, then the arithmetic.
+    //   KEND = 0: no unit ends inside the batch (straight-line FMAs)
+    //   KEND = k in 1..kSPS (full batches only): the current unit ends with the batch's k-th step and the next
+    //             one does not end inside the batch -- the flush sits at a fixed place, no per-step test
+    //   KEND < 0: generic (partial batches at the end of a run / segment, units shorter than a batch)
+    auto batch = [&](auto kend_tag, int cnt) {
+      constexpr int KEND = decltype(kend_tag)::value;
+      constexpr bool FULL = KEND >= 0;
+      const uint32_t st = ring_lane + uint32_t(slot) * uint32_t(kStageBytes);
       uint32_t ent[kSPS];
       uint32_t cw[kSPS][4], rw[kSPS][4];
       uint16_t xh[kSPS];
@@ -368,43 +401,75 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
       for (int j = 0; j < kSPS; ++j) {
         if (FULL || j < cnt) {
           // entry = index12 | column12 << 12 | residual8 << 24; x_base is 8 KiB aligned, so `|` adds
-          lds_entry<8>(cw[j], slice_base + ((ent[j] & 0xfffu) << 4));
-          if constexpr (RES) lds_entry<8>(rw[j], res_lane + ((ent[j] >> 24) << 7));
+          lds_entry<8>(cw[j], mad_u32(ent[j] & 0xfffu, 16u, slice_base));
+          if constexpr (RES) lds_entry<8>(rw[j], mad_u32(ent[j] >> 24, 128u, res_lane));
           xh[j] = lds_u16(x_base | ((ent[j] >> 11) & 0x1ffeu));
         }
       }
+      if constexpr (KEND == 0) {
 #pragma unroll
-      for (int j = 0; j < kSPS; ++j) {
-        if (FULL || j < cnt) {
-          const bool last = t + 1 == u_end;  // last step of the unit: mask the padding entries
+        for (int j = 0; j < kSPS; ++j) fma_entry<T, RES>(acc, xh[j], cw[j], rw[j]);
+        t += kSPS;
+      } else if constexpr (KEND > 0) {
+#pragma unroll
+        for (int j = 0; j < kSPS; ++j) {
           uint16_t xv = xh[j];
-          if (last && uint32_t(lane) >= tail) xv = 0;
+          if (j == KEND - 1 && uint32_t(lane) >= tail) xv = 0;  // last step of the unit: mask the padding entries
           fma_entry<T, RES>(acc, xv, cw[j], rw[j]);
-          ++t;
-          if (last) {
+          if (j == KEND - 1) {
             flush(true);
-            ++u;
-            if (u < nun) {
-              u_end = int(s_tab[u + 1] & kStepMask);
-              tail = s_tab[u] >> 26;
+            advance();
+          }
+        }
+        t += kSPS;
+      } else {
+#pragma unroll
+        for (int j = 0; j < kSPS; ++j) {
+          if (j < cnt) {
+            const bool last = t + 1 == u_end;
+            uint16_t xv = xh[j];
+            if (last && uint32_t(lane) >= tail) xv = 0;
+            fma_entry<T, RES>(acc, xv, cw[j], rw[j]);
+            ++t;
+            if (last) {
+              flush(true);
+              advance();
             }
           }
         }
       }
     };
-    for (int qi = 0; qi < nstage; ++qi) {
-      int cnt;
-      stage_at(qi, t, cnt);
-      const bool segB = qi >= n1;
-      slice_base = smem_u32(s_slice) + (segB ? uint32_t(kSliceBytes) : 0u);
-      x_base = s_x + ((segB && xB_own) ? 8192u : 0u);
-      cb = segB ? cbiasB : cbiasA;
-      mbar_wait(&full[slot], par);
-      if (cnt == kSPS) stage_body(std::true_type{}, cnt);
-      else stage_body(std::false_type{}, cnt);
-      __syncwarp();  // every lane has read its words of the stage: refill it
-      if (qi + stages < nstage) issue(qi + stages, slot);
-      if (++slot == stages) slot = 0, par ^= 1u;
+#pragma unroll 1
+    for (int part = 0; part < 2; ++part) {
+      // part 0 = this run's steps in segment A, part 1 = its steps in segment B (a stage never straddles both)
+      const int np = part ? n2 : n1;
+      if (np == 0) continue;
+      t = part ? b2 : t_begin;
+      const int pe = part ? t_end : e1;
+      slice_base = smem_u32(s_slice) + (part ? uint32_t(kSliceBytes) : 0u);
+      x_base = s_x + ((part && xB_own) ? 8192u : 0u);
+      cb = part ? cbiasB : cbiasA;
+#pragma unroll 1
+      for (int si = 0; si < np; ++si, ++qi) {
+        const int cnt = min(kSPS, pe - t);
+        mbar_wait(&full[slot], par);
+        const int k = u_end - t;  // steps left in the current unit (>= 1)
+        if (cnt == kSPS && k > kSPS) {
+          batch(std::integral_constant<int, 0>{}, cnt);
+        } else if (cnt == kSPS && !(u + 1 < nun && int(s_tab[u + 2] & kStepMask) - t <= kSPS)) {
+          switch (k) {
+            case 1: batch(std::integral_constant<int, 1>{}, cnt); break;
+            case 2: batch(std::integral_constant<int, 2>{}, cnt); break;
+            case 3: batch(std::integral_constant<int, 3>{}, cnt); break;
+            default: batch(std::integral_constant<int, 4>{}, cnt); break;
+          }
+        } else {
+          batch(std::integral_constant<int, -1>{}, cnt);
+        }
+        __syncwarp();  // every lane has read its words of the stage: refill it
+        if (qi + stages < nstage) issue(qi + stages, slot);
+        if (++slot == stages) slot = 0, par ^= 1u;
+      }
     }
     // the run ended inside a unit: its sums so far are this warp's piece of that unit
     if (u < nun && int(s_tab[u] & kStepMask) < t_end) flush(false);
@@ -433,7 +498,7 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
           if (pj != un) break;
           v += s_piece[j * 8 + e];
         }
-        L.part[size_t(u0 + un) * 8 + e] = v + (un >= nA ? cbiasB : cbiasA);
+        red_add_fixed(L.yacc + size_t(un < nA ? rA0 + un : un - nA) * 8 + e, v + (un >= nA ? cbiasB : cbiasA));
       }
     }
   }
@@ -442,7 +507,7 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
 
   // -------- arrival: every row block this CTA's units belong to learns how many of them are done -----------
   {
-    const int rA0 = u0 - cA * Ro, rA1 = rA0 + nA, nB = nun - nA;
+    const int rA1 = rA0 + nA, nB = nun - nA;
     const int nbA = (rA1 - 1) / kRB - rA0 / kRB + 1;
     const int nbB = two ? (nB - 1) / kRB + 1 : 0;
     if (tid < nbA + nbB) {
@@ -458,26 +523,19 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   stamp(8);
   const int nd = *s_ndone;
   if (nd > 0) {
-    // this CTA's arrival completed nd row blocks: add the Q partials of every row in combo order
+    // this CTA's arrival completed nd row blocks: every unit of their rows has added its sums
     __threadfence();
     const T* bias = reinterpret_cast<const T*>(L.bias);
     T* y = reinterpret_cast<T*>(L.y);
-    const int Q = L.Q;
     for (int i = tid; i < nd * kRB * 8; i += kLT) {
       const int b = s_done[i / (kRB * 8)], rr = i % (kRB * 8);
-      const int r = b * kRB + (rr >> 3), e = rr & 7, o = r * 8 + e;
-      if (r < Ro && o < L.O) {
-        float v = bias ? DT<T>::to_float(bias[o]) : 0.f;
-        const float* p = L.part + size_t(r) * 8 + e;
-        const size_t cstride = size_t(Ro) * 8;
-        int c = 0;
-        for (; c + 4 <= Q; c += 4) {
-          const float a0 = ldg_cg_f32(p + size_t(c) * cstride), a1 = ldg_cg_f32(p + size_t(c + 1) * cstride);
-          const float a2 = ldg_cg_f32(p + size_t(c + 2) * cstride), a3 = ldg_cg_f32(p + size_t(c + 3) * cstride);
-          v = (((v + a0) + a1) + a2) + a3;
-        }
-        for (; c < Q; ++c) v += ldg_cg_f32(p + size_t(c) * cstride);
-        y[o] = DT<T>::from_float(v);
+      const int r = b * kRB + (rr >> 3), o = r * 8 + (rr & 7);
+      if (r < Ro) {
+        unsigned long long* p = L.yacc + o;
+        long long q;
+        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(q) : "l"(p) : "memory");
+        *p = 0ull;  // zero at rest for the next launch
+        if (o < L.O) y[o] = DT<T>::from_float(float(q) * kFixInv + (bias ? DT<T>::to_float(bias[o]) : 0.f));
       }
     }
     if (tid < nd) L.counters[s_done[tid]] = 0u;  // leave the counters zeroed for the next launch
@@ -518,10 +576,8 @@ bool gemv_lists_eligible(const vptq_linear_desc& d) {
 }
 
 size_t gemv_lists_workspace_bytes(const vptq_linear_desc& d) {
-  if (!gemv_lists_eligible(d)) return 0;
-  const size_t Ro = size_t((d.out_features + 7) / 8);
-  const size_t Q = size_t(d.num_centroids / kSliceEntries) * size_t((d.in_features + d.lists_tile_cols - 1) / d.lists_tile_cols);
-  return kCounterRegionBytes + Q * Ro * 32;
+  // counters and accumulators both live in the fixed zero-at-rest head of the workspace
+  return gemv_lists_eligible(d) ? kZeroRegionBytes : 0;
 }
 
 int gemv_lists_launch(int n, const vptq_linear_desc* const* descs, const void* x, void* const* ys, uint32_t flags,
@@ -596,17 +652,22 @@ int gemv_lists_launch(int n, const vptq_linear_desc* const* descs, const void* x
     }
   }
   int max_nun = 0, max_kr = 0;
-  size_t ws_need = kCounterRegionBytes;
+  size_t ws_need = kZeroRegionBytes;
+  size_t rows_total = 0;
   size_t nblk = 0;
   for (int l = 0; l < n; ++l) {
     const int64_t U = int64_t(Q) * Ro[l];
     max_nun = std::max<int>(max_nun, int((U + share[l] - 1) / share[l]));
     max_kr = std::max(max_kr, descs[l]->num_res_centroids > 0 ? descs[l]->num_res_centroids : 0);
-    ws_need += size_t(U) * 32;
+    rows_total += size_t(Ro[l]);
     nblk += size_t((Ro[l] + kRB - 1) / kRB);
   }
   if (max_nun > kMaxWindow) {
     set_error("gemv_lists: %d units per CTA exceed %d", max_nun, kMaxWindow);
+    return VPTQ_ERR_UNSUPPORTED;
+  }
+  if (rows_total > size_t(kMaxIndexRows)) {
+    set_error("gemv_lists: %zu index rows exceed %d", rows_total, kMaxIndexRows);
     return VPTQ_ERR_UNSUPPORTED;
   }
   if (!workspace || workspace_bytes < ws_need || nblk * 4 > kCounterRegionBytes) {
@@ -646,6 +707,15 @@ int gemv_lists_launch(int n, const vptq_linear_desc* const* descs, const void* x
   }
 
   mp.n = n, mp.x = x, mp.prof = gemv_profile_buffer();
+  if (mp.prof) {
+    // developer aid: VPTQ_B200_PROF_SLOTS=N gives every launch its own 32-stamp record (round robin over N)
+    static const int slots = [] {
+      const char* e = std::getenv("VPTQ_B200_PROF_SLOTS");
+      return e ? std::max(1, std::atoi(e)) : 1;
+    }();
+    static std::atomic<unsigned> counter{0};
+    if (slots > 1) mp.prof += 32u * (counter.fetch_add(1) % unsigned(slots));
+  }
   uint32_t begin = 0;
   uint8_t* wsb = reinterpret_cast<uint8_t*>(workspace);
   size_t part_off = kCounterRegionBytes, ctr_off = 0;
@@ -659,9 +729,9 @@ int gemv_lists_launch(int n, const vptq_linear_desc* const* descs, const void* x
     L.I = I, L.O = d.out_features, L.Ro = Ro[l], L.Kr = d.num_res_centroids > 0 ? d.num_res_centroids : 0;
     L.NS = NS, L.Q = Q, L.TCW = TCW, L.U = Q * Ro[l];
     L.ncta = share[l];
-    L.part = reinterpret_cast<float*>(wsb + part_off);
+    L.yacc = reinterpret_cast<unsigned long long*>(wsb + part_off);
     L.counters = reinterpret_cast<uint32_t*>(wsb + ctr_off);
-    part_off += size_t(L.U) * 32;
+    part_off += size_t(Ro[l]) * 64;
     ctr_off += size_t((Ro[l] + kRB - 1) / kRB) * 4;
     mp.grid_begin[l] = begin;
     begin += uint32_t(share[l]);

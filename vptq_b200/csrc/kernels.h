@@ -28,12 +28,14 @@ static inline int ilog2(int64_t v) {
 }
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// Workspace convention shared by every op: bytes [0, kCounterRegionBytes) hold the GEMV's split-K
-// row counters and are the ONLY part that must be zero at rest; everything behind is scratch that
-// each op overwrites before reading.  The region's extent is fixed so that it never depends on
+// Workspace convention shared by every op: bytes [0, kZeroRegionBytes) are the ONLY part that must be zero
+// at rest (kernels leave them zeroed): first kCounterRegionBytes of uint32 arrival / split-K row counters, then
+// 64 bytes per index row of 64-bit fixed-point output accumulators (list-based decode GEMV).  Everything behind
+// is scratch that each op overwrites before reading.  The region's extent is fixed so that it never depends on
 // which layer used the workspace last.
 constexpr int kMaxIndexRows = 65536;
 constexpr size_t kCounterRegionBytes = size_t(kMaxIndexRows) * 4;
+constexpr size_t kZeroRegionBytes = kCounterRegionBytes + size_t(kMaxIndexRows) * 64;
 
 // -------------------------------------------------------------------------------------------
 // decode GEMV
