@@ -238,10 +238,18 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
     mbar_init(&bars[tid], 1);
     fence_mbar_init();
   }
-  // residual codebook (<= 256 entries of 16 bytes): one entry per thread, stored 8 times below
-  uint4 res_entry = make_uint4(0u, 0u, 0u, 0u);
+  // residual codebook (<= 256 entries of 16 bytes), stored 8 times: copy k of entry i sits at 16-byte slot
+  // i*8 + k and lane L reads copy L mod 8, so the 8 lanes of a quarter-warp always hit 8 different bank groups.
+  // Thread t fills slots t, t + 512, ...: consecutive lanes write consecutive slots (conflict-free stores).
+  uint4 res_entry[(256 * kResRep) / kLT];
   if constexpr (RES) {
-    if (tid < L.Kr) res_entry = ldg_nc_v4(reinterpret_cast<const uint8_t*>(L.res_centroids) + tid * 16, pol_keep);
+#pragma unroll
+    for (int j = 0; j < (256 * kResRep) / kLT; ++j) {
+      const int slot = tid + j * kLT;
+      res_entry[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (slot < L.Kr * kResRep)
+        res_entry[j] = ldg_nc_v4(reinterpret_cast<const uint8_t*>(L.res_centroids) + (slot / kResRep) * 16, pol_keep);
+    }
   }
   // list table of this CTA's units
   for (int i = tid; i <= nun; i += kLT) s_tab[i] = L.tab[u0 + i];
@@ -301,13 +309,11 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   if (colB) xb = load8<T>(x, fB, fBend, 0);
   for (int qi = 0; qi < min(stages, nstage); ++qi) issue(qi, qi);
 
-  // -------- residual codebook: copy k of entry i sits at 16-byte slot i*8 + k and lane L reads copy L mod 8,
-  // so the 8 lanes of a quarter-warp always hit 8 different bank groups ----------------------------------
   if constexpr (RES) {
-    if (tid < L.Kr) {
-      const uint32_t dst = smem_u32(s_res) + uint32_t(tid) * (16u * kResRep);
 #pragma unroll
-      for (int c = 0; c < kResRep; ++c) sts_v4(dst + uint32_t(c) * 16u, res_entry);
+    for (int j = 0; j < (256 * kResRep) / kLT; ++j) {
+      const int slot = tid + j * kLT;
+      if (slot < L.Kr * kResRep) sts_v4(smem_u32(s_res) + uint32_t(slot) * 16u, res_entry[j]);
     }
   }
   stamp(3);
@@ -527,15 +533,30 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
     __threadfence();
     const T* bias = reinterpret_cast<const T*>(L.bias);
     T* y = reinterpret_cast<T*>(L.y);
-    for (int i = tid; i < nd * kRB * 8; i += kLT) {
-      const int b = s_done[i / (kRB * 8)], rr = i % (kRB * 8);
-      const int r = b * kRB + (rr >> 3), o = r * 8 + (rr & 7);
-      if (r < Ro) {
-        unsigned long long* p = L.yacc + o;
-        long long q;
-        asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(q) : "l"(p) : "memory");
-        *p = 0ull;  // zero at rest for the next launch
-        if (o < L.O) y[o] = DT<T>::from_float(float(q) * kFixInv + (bias ? DT<T>::to_float(bias[o]) : 0.f));
+    constexpr int kFB = 8;  // outputs per thread whose loads are in flight together
+    for (int i0 = tid; i0 < nd * kRB * 8; i0 += kFB * kLT) {
+      long long q[kFB];
+      int o[kFB];
+#pragma unroll
+      for (int k = 0; k < kFB; ++k) {
+        const int i = i0 + k * kLT;
+        o[k] = -1;
+        q[k] = 0;
+        if (i < nd * kRB * 8) {
+          const int b = s_done[i / (kRB * 8)], rr = i % (kRB * 8);
+          const int r = b * kRB + (rr >> 3);
+          if (r < Ro) {
+            o[k] = r * 8 + (rr & 7);
+            asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(q[k]) : "l"(L.yacc + o[k]) : "memory");
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kFB; ++k) {
+        if (o[k] >= 0) {
+          L.yacc[o[k]] = 0ull;  // zero at rest for the next launch
+          if (o[k] < L.O) y[o[k]] = DT<T>::from_float(float(q[k]) * kFixInv + (bias ? DT<T>::to_float(bias[o[k]]) : 0.f));
+        }
       }
     }
     if (tid < nd) L.counters[s_done[tid]] = 0u;  // leave the counters zeroed for the next launch
