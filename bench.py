@@ -36,12 +36,27 @@ sys.path.insert(0, ROOT)
 LLAMA3_8B = dict(name="llama3-8b", layers=32, hidden=4096, kv=1024, ffn=14336)
 QUANT = dict(vector_len=8, num_centroids=65536, num_res_centroids=256)
 METRIC = "decode tokens/sec Llama-3-8B 2-bit (VPTQ v8-k65536-256, b=24 index bits / 8 weights), batch 1"
+# BASELINE.json configs[3]: Llama-3-70B, true 2-bit variant (K = 65536, no residual codebook: b = 16)
+LLAMA3_70B = dict(name="llama3-70b", layers=80, hidden=8192, kv=1024, ffn=28672)
+QUANT_70B = dict(vector_len=8, num_centroids=65536, num_res_centroids=-1)
+MODELS = {"llama3-8b": (LLAMA3_8B, QUANT, METRIC, "BASELINE.json configs[1]"),
+          "llama3-70b": (LLAMA3_70B, QUANT_70B,
+                         "decode tokens/sec Llama-3-70B 2-bit (VPTQ v8-k65536-0, b=16 index bits / 8 weights), batch 1",
+                         "BASELINE.json configs[3]")}
 
 
 def model_linears(m):
     h, kv, f = m["hidden"], m["kv"], m["ffn"]
     # (name, in, out, input_of)
     return [("q", h, h), ("k", h, kv), ("v", h, kv), ("o", h, h), ("gate", h, f), ("up", h, f), ("down", f, h)]
+
+
+def workload_string(m, q, cfg_name):
+    Kr = q["num_res_centroids"]
+    b = (q["num_centroids"].bit_length() - 1) + (Kr.bit_length() - 1 if Kr > 0 else 0)
+    return (f"{cfg_name}: {m['name']} decode batch=1 seq=1, all {7 * m['layers']} VPTQ linears ({m['layers']} layers x "
+            f"q,k,v,o,gate,up,down), v=8 K={q['num_centroids']} Kr={max(Kr, 0)} (b={b}), perm+norm on; "
+            "attention/norm/lm_head not on the VPTQ path and not executed")
 
 
 def algorithmic_bytes(m, q, tokens=1, world=1):
@@ -99,41 +114,76 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def build_stack(m, q, device, rank, world, dtype):
-    """Random weights for this rank's out_features shard of every linear; returns layer dicts."""
+def layer_tensors(m, q, li, name, i, o, device, dtype, rows=None):
+    """Synthetic tensors of linear `name` of decoder layer `li`: a function of (li, name) only, so every rank
+    (and the unsharded correctness check) sees the same layer; `rows` = (r0, r1) keeps that slice of the
+    index rows (tensor parallelism shards out_features, tp.shard_bounds)."""
     import torch
-    from vptq_b200 import native
     v, K, Kr = q["vector_len"], q["num_centroids"], q["num_res_centroids"]
     ib, rb = K.bit_length() - 1, max(Kr.bit_length() - 1, 0)
-    g = torch.Generator(device=device).manual_seed(1234 + rank)
+    ro, wd = o // v, (i * (ib + rb) + 31) // 32
+    g = torch.Generator(device=device).manual_seed(1234 + 16 * li + [n for n, _, _ in model_linears(m)].index(name))
+    t = dict(
+        indices=torch.randint(-2 ** 31, 2 ** 31 - 1, (1, ro, wd), device=device, dtype=torch.int32, generator=g),
+        # std 1/sqrt(in): unit gain, so activations stay O(1) through the chained layers
+        centroids=(torch.randn(1, K * v, device=device, generator=g) / i ** 0.5).to(dtype),
+        res_centroids=(0.25 * torch.randn(1, Kr * v, device=device, generator=g) / i ** 0.5).to(dtype) if Kr > 0 else None,
+        # uint16 payload behind an int16 view: int64 -> int16 narrowing keeps the low 16 bits
+        perm=torch.randperm(i, device=device, generator=g).to(torch.int16),
+        weight_scale=(1 + 0.1 * torch.randn(i, device=device, generator=g)).to(dtype),
+        weight_bias=(0.01 * torch.randn(i, device=device, generator=g) / i ** 0.5).to(dtype))
+    if rows is not None:
+        t["indices"] = t["indices"][:, rows[0]:rows[1], :].contiguous()
+    return t
+
+
+def make_layer_desc(q, t, i, o_loc, dtype, lists=None):
+    from vptq_b200 import native
+    return native.make_desc(
+        dtype=dtype, in_features=i, out_features=o_loc, vector_len=q["vector_len"], num_centroids=q["num_centroids"],
+        num_res_centroids=q["num_res_centroids"], num_codebooks=1, group_size=i, outlier_size=0, outlier_vector_len=-1,
+        num_outlier_centroids=-1, indices=t["indices"], centroids=t["centroids"], res_centroids=t["res_centroids"],
+        outlier_indices=None, outlier_centroids=None, perm=t["perm"], weight_scale=t["weight_scale"],
+        weight_bias=t["weight_bias"], bias=None, lists=lists)
+
+
+def build_stack(m, q, device, rank, world, dtype):
+    """This rank's out_features shard of every linear; returns layer dicts."""
+    v = q["vector_len"]
     stack = []
     for li in range(m["layers"]):
         layer = {}
         for name, i, o in model_linears(m):
             o_loc = o // world
-            ro, wd = o_loc // v, (i * (ib + rb) + 31) // 32
-            t = dict(
-                indices=torch.randint(-2 ** 31, 2 ** 31 - 1, (1, ro, wd), device=device, dtype=torch.int32, generator=g),
-                # std 1/sqrt(in): unit gain, so activations stay O(1) through 224 chained layers
-                centroids=(torch.randn(1, K * v, device=device, generator=g) / i ** 0.5).to(dtype),
-                res_centroids=(0.25 * torch.randn(1, Kr * v, device=device, generator=g) / i ** 0.5).to(dtype),
-                # uint16 payload behind an int16 view: int64 -> int16 narrowing keeps the low 16 bits
-                perm=torch.randperm(i, device=device, generator=g).to(torch.int16),
-                weight_scale=(1 + 0.1 * torch.randn(i, device=device, generator=g)).to(dtype),
-                weight_bias=(0.01 * torch.randn(i, device=device, generator=g) / i ** 0.5).to(dtype))
-            t["desc"] = native.make_desc(
-                dtype=dtype, in_features=i, out_features=o_loc, vector_len=v, num_centroids=K, num_res_centroids=Kr,
-                num_codebooks=1, group_size=i, outlier_size=0, outlier_vector_len=-1, num_outlier_centroids=-1,
-                indices=t["indices"], centroids=t["centroids"], res_centroids=t["res_centroids"], outlier_indices=None,
-                outlier_centroids=None, perm=t["perm"], weight_scale=t["weight_scale"], weight_bias=t["weight_bias"],
-                bias=None, lists=None if world == 1 else False)   # tensor-parallel launches use the generic kernel
-            if os.environ.get("BENCH_DEBUG"):
-                pv = t["perm"].view(torch.uint16).to(torch.int64)
-                assert int(pv.max()) == i - 1 and int(pv.min()) == 0 and pv.unique().numel() == i, "bad perm"
+            t = layer_tensors(m, q, li, name, i, o, device, dtype, rows=(rank * o_loc // v, (rank + 1) * o_loc // v))
+            t["desc"] = make_layer_desc(q, t, i, o_loc, dtype)
             t["in"], t["out"], t["out_loc"] = i, o, o_loc
             layer[name] = t
         stack.append(layer)
     return stack
+
+
+def reference_hidden(m, q, device, dtype, x_in):
+    """The same token through the UNSHARDED layers on this GPU alone (one decoder layer resident at a time):
+    what the tensor-parallel exchange must reproduce.  Same kernels, same chain as make_step."""
+    import torch
+    from vptq_b200 import native
+    h, kv, f = m["hidden"], m["kv"], m["ffn"]
+    x = x_in.clone()
+    for li in range(m["layers"]):
+        out = {}
+        src = {"q": "x", "k": "x", "v": "x", "o": "q", "gate": "o", "up": "o", "down": "gate"}
+        out["x"] = x
+        for name, i, o in model_linears(m):
+            t = layer_tensors(m, q, li, name, i, o, device, dtype)
+            d = make_layer_desc(q, t, i, o, dtype)
+            y = torch.empty(1, o, device=device, dtype=dtype)
+            native.quant_gemv(d, out[src[name]], y)
+            torch.cuda.synchronize()
+            out[name] = y
+            del d, t
+        x = out["down"]
+    return x
 
 
 def make_step(m, stack, device, dtype, rank, world, flags, tp_mode="nccl"):
@@ -287,7 +337,8 @@ def run_ours(args):
     _log("process group up")
     native.lib()
     dtype = torch.float16
-    m, q = dict(LLAMA3_8B), QUANT
+    m, q, metric, cfg_name = MODELS[args.model]
+    m = dict(m)
     if args.debug_layers:
         m["layers"] = args.debug_layers
     flags = 0 if args.no_pdl else native.FLAG_PDL
@@ -295,20 +346,30 @@ def run_ours(args):
     stack = build_stack(m, q, device, rank, world, dtype)
     _log("weights built")
     tp_mode = args.tp_mode if world > 1 else "none"
+    torch.manual_seed(4321)
+    x_host = torch.randn(1, m["hidden"]).to(dtype).pin_memory()
+    tp_fallback = None
     if tp_mode == "p2p":
-        # peer-mapped activations need symmetric memory; every rank must take the same decision
+        # peer-mapped activations need symmetric memory, and the fused exchange must get through one eager
+        # token without a refused launch or a flag time-out; every rank must take the same decision
         ok = torch.ones(1, device=device)
         try:
             x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags, "p2p")
+            x_in.copy_(x_host, non_blocking=True)
+            step()
+            torch.cuda.synchronize()
+            if int(step.tp_error.item()) != 0:
+                raise RuntimeError("a tensor-parallel flag wait timed out")
         except Exception as e:  # noqa: BLE001
             _log(f"p2p exchange unavailable ({e!r}); falling back to NCCL all-reduce")
+            tp_fallback = repr(e)[:200]
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if float(ok.item()) == 0.0:
-            tp_mode = "nccl"
+            tp_mode, tp_fallback = "nccl", tp_fallback or "another rank could not set up the fused exchange"
+            torch.cuda.synchronize()
     if tp_mode != "p2p":
         x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags, tp_mode)
-    x_host = torch.randn(1, m["hidden"]).to(dtype).pin_memory()
     y_host = torch.empty(1, m["hidden"], dtype=dtype).pin_memory()
 
     s = torch.cuda.Stream(device)
@@ -356,8 +417,13 @@ def run_ours(args):
         ms = ev[0].elapsed_time(ev[1])
         clk = clocks.stop() if rank == 0 else None
         assert torch.isfinite(h_out.float()).all(), "activations overflowed"
-        if step.tp_error is not None:
-            assert int(step.tp_error.item()) == 0, "a tensor-parallel flag wait timed out"
+        tp_err = int(step.tp_error.item()) if step.tp_error is not None else 0
+        if world > 1:
+            te = torch.tensor([tp_err], device=device)
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            tp_err = int(te.item())
+        assert tp_err == 0, "a tensor-parallel flag wait timed out"
+        h_final = h_out.clone()
 
         # ---- `e2e`: host buffers, H2D + D2H inside the timed region, per-step sync ------------------
         e2e_steps = args.steps
@@ -383,6 +449,26 @@ def run_ours(args):
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms, ms_e2e = tms.tolist()
 
+    # ---- correctness of the measured computation: the same token through the unsharded layers on rank 0
+    # alone (N > 1: checks the tensor-parallel exchange; N = 1: the list kernel against the generic one) ----
+    lists_on = os.environ.get("VPTQ_B200_LISTS", native.LISTS_DEFAULT) != "0" and \
+        "lists=0" not in os.environ.get("VPTQ_B200_GEMV_TUNE", "")
+    check = None
+    if rank == 0 and not args.no_check:
+        with torch.cuda.stream(s):
+            x_chk = torch.empty(1, m["hidden"], device=device, dtype=dtype)
+            x_chk.copy_(x_host)
+            if world == 1:
+                os.environ["VPTQ_B200_LISTS"] = "0" if os.environ.get("VPTQ_B200_LISTS", "1") != "0" else "1"
+            h_ref = reference_hidden(m, q, device, dtype, x_chk).float()
+            s.synchronize()
+        err = float((h_final.float() - h_ref).abs().max() / h_ref.abs().max())
+        # 4 * layers chained 16-bit roundings: the bar is loose, a wrong or stale slice misses it by orders of magnitude
+        check = {"max_rel_err": round(err, 6), "ok": bool(err <= 2e-2), "against":
+                 "unsharded layers on rank 0" if world > 1 else "the other decode kernel (generic <-> lists), same token"}
+    if world > 1:
+        dist.barrier()
+
     if rank == 0:
         ms_step = ms / args.steps
         value = 1e3 / ms_step
@@ -395,21 +481,17 @@ def run_ours(args):
         abytes = algorithmic_bytes(m, q, 1, world)         # per rank and step
         achieved = abytes / (ms_step * 1e-3) / 1e9
         traffic = None
-        # single-GPU decode runs the list-based kernel (tensor-parallel launches use the generic one)
-        sliced_on = world == 1 and os.environ.get("VPTQ_B200_LISTS", native.LISTS_DEFAULT) != "0" and \
-            "lists=0" not in os.environ.get("VPTQ_B200_GEMV_TUNE", "")
+        sliced_on = lists_on
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "gemv_traffic.json")))
             traffic = (tj["sliced"] if sliced_on else tj)["dram_bytes_per_token"] // (n_launch * world)
         except Exception:
             pass
         line = {
-            "metric": METRIC, "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
+            "metric": metric, "value": round(value, 2), "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "BASELINE.json configs[1]: Llama-3-8B decode batch=1 seq=1, all 224 VPTQ linears "
-                                   "(32 layers x q,k,v,o,gate,up,down), v=8 K=65536 Kr=256 (b=24), perm+norm on; "
-                                   "attention/norm/lm_head not on the VPTQ path and not executed",
+            "config": {"workload": workload_string(m, q, cfg_name),
                        "parallelism": (f"tp{world} (out_features sharded; " +
                                        ("exchange fused into the GEMV: NVLink peer stores + epoch flags, no NCCL call"
                                         if tp_mode == "p2p" else "1 NCCL all-reduce per launch: q|k|v, o, gate|up, down") + ")")
@@ -433,6 +515,18 @@ def run_ours(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
             "clocks": clk,
         }
+        if world > 1:
+            line["tp_check"] = check
+            line["config"]["tp_mode"] = tp_mode
+            if tp_fallback:
+                line["config"]["tp_fallback_reason"] = tp_fallback
+        else:
+            line["check"] = check
+        if world == 1 and not args.no_ref_cuda:
+            try:
+                line["ref_cuda"] = ref_cuda_timing(m, q, device, dtype)
+            except Exception as e:  # noqa: BLE001
+                line["ref_cuda"] = {"unavailable": repr(e)[:300]}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(m, q, budget_s=args.cpu_budget)
         print(json.dumps(line), flush=True)
@@ -449,55 +543,140 @@ def run_ours(args):
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the reference's pure-torch path (ported, see oracle/torch_port.py) on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(m, q, budget_s=20.0, min_reps=2):
-    """Bounded sample: the q_proj-shaped linear (4096x4096, b=24) of the same workload, batch 1."""
+def _cpu_threads():
+    """All the host threads this process may use: torchrun pins OMP_NUM_THREADS=1, which would make the CPU arm
+    look 60x slower than the box really is -- undo it (rank 0 is the only rank that runs the CPU arm)."""
+    import torch
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        torch.set_num_threads(max(1, n))
+    except Exception:
+        pass
+    return torch.get_num_threads()
+
+
+_CPU_LAYERS = {}
+
+
+def cpu_baseline(m, q, budget_s=20.0, min_reps=1):
+    """Bounded sample: ONE decoder layer's seven VPTQ linears (q,k,v,o,gate,up,down at their real shapes) of the
+    same workload, batch 1 = 1/layers of a token, through the reference's pure-torch path (oracle/torch_port.py)."""
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch_port as tp
-    h = m["hidden"]
-    L = tp.synthetic_layer(h, h, q["vector_len"], q["num_centroids"], q["num_res_centroids"], seed=0)
-    x = torch.randn(1, h).to(torch.float16)
-    tp.quant_gemm(x, L)                                   # warm-up
+    threads = _cpu_threads()
+    key = (m["name"], q["num_centroids"], q["num_res_centroids"])
+    if key not in _CPU_LAYERS:
+        _CPU_LAYERS[key] = [(tp.synthetic_layer(i, o, q["vector_len"], q["num_centroids"], q["num_res_centroids"], seed=k),
+                             torch.randn(1, i).to(torch.float16)) for k, (_, i, o) in enumerate(model_linears(m))]
+    layers = _CPU_LAYERS[key]
     times, t_start = [], time.perf_counter()
     while len(times) < min_reps or (time.perf_counter() - t_start < budget_s and len(times) < 50):
         t0 = time.perf_counter()
-        tp.quant_gemm(x, L)
+        for L, x in layers:
+            tp.quant_gemm(x, L)
         times.append(time.perf_counter() - t0)
     t = statistics.median(times)
-    fields_sample = (h // q["vector_len"]) * h
-    fields_token = sum((o // q["vector_len"]) * i for _, i, o in model_linears(m)) * m["layers"]
-    tok_s = 1.0 / (t * fields_token / fields_sample)
-    return {"value": round(tok_s, 5), "unit": "tokens/s", "cores": torch.get_num_threads(), "kind": "port",
-            "host_cpus": os.cpu_count(),
-            "sample": f"one 4096x4096 v8-k65536-256 linear (1/{fields_token / fields_sample:.1f} of a token's index "
-                      f"fields), median of {len(times)} calls of {t * 1e3:.0f} ms, scaled to a full token; "
-                      "oracle/torch_port.py = reference torch fallback (unpack + gather + F.linear) in fp32"}
+    tok_s = 1.0 / (t * m["layers"])
+    return {"value": round(tok_s, 5), "unit": "tokens/s", "cores": threads, "kind": "port", "host_cpus": os.cpu_count(),
+            "sample": f"one decoder layer of {m['name']} (its 7 VPTQ linears at full size = 1/{m['layers']} of a token), "
+                      f"median of {len(times)} passes of {t:.2f} s, scaled to a full token; oracle/torch_port.py = "
+                      "reference torch fallback (unpack + gather + F.linear) in fp32"}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    m, q = LLAMA3_8B, QUANT
-    steps = max(args.steps, 1)
-    per_step_budget = min(20.0, 150.0 / (steps + max(args.warmup, 1)))
-    cb = None
-    vals = []
-    for i in range(max(args.warmup, 1) + steps):
-        cb = cpu_baseline(m, q, budget_s=per_step_budget * 0.8, min_reps=1)
-        if i >= max(args.warmup, 1):
+    m, q, metric, cfg_name = MODELS[args.model]
+    steps, warm = max(args.steps, 1), max(args.warmup, 1)
+    cb, vals = None, []
+    t_begin = time.perf_counter()
+    for i in range(warm + steps):
+        cb = cpu_baseline(m, q, budget_s=0.0, min_reps=1)             # one pass over the layer per step
+        if i >= warm:
             vals.append(cb["value"])
+        if time.perf_counter() - t_begin > 240 and len(vals) >= 3:    # keep the whole run within minutes
+            break
     v = statistics.median(vals)
     cb["value"] = v
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": max(args.warmup, 1), "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": metric, "value": v, "unit": "tokens/s", "n_gpus": args.gpus, "steps": len(vals),
+        "warmup": warm, "ms_per_step": round(1e3 / v, 1), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "BASELINE.json configs[1] (same as --impl ours); each step = a bounded sample "
-                               "(one 4096x4096 linear) scaled to a whole token"},
+        "config": {"workload": workload_string(m, q, cfg_name),
+                   "sample": "each step = one decoder layer (7 linears) timed on the host cores, scaled to a whole token"},
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU-vs-GPU bar: the reference's OWN CUDA kernels (oracle/_ref/libvptq.so, unmodified sources compiled for
+# sm_100a by oracle/build_ref.sh) timed on the same box, eager, one launch pair per linear as the reference runs
+# them (csrc/quant_gemv.cu:241-294 + its sum(-1) epilogue; prefill: csrc/dequant.cu:227-287 + F.linear).
+# ------------------------------------------------------------------------------------------------
+def ref_cuda_timing(m, q, device, dtype, prefill_tokens=8192):
+    import importlib.util
+    import torch
+    so = os.path.join(ROOT, "oracle", "_ref", "libvptq.so")
+    if not os.path.exists(so):
+        return {"unavailable": "oracle/_ref/libvptq.so not built (oracle/build_ref.sh needs /root/reference)"}
+    try:
+        spec = importlib.util.spec_from_file_location("libvptq", so)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"cannot load oracle/_ref/libvptq.so: {e!r}"[:200]}
+    v = q["vector_len"]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > L2: every timed launch streams from HBM
+    out = {"us_per_shape": {}, "how": "CUDA events around quant_gemv (kernel + sum(-1)), L2 flushed before each call, "
+                                      "median of 7; tokens_per_s = 1 / (sum over the 7 linears x layers), eager launches "
+                                      "excluded (kernel time only: favourable to the reference)"}
+    per_layer_us = 0.0
+    shapes = {}
+    for name, i, o in model_linears(m):
+        shapes.setdefault((i, o), []).append(name)
+    prefill = {}
+    for (i, o), names in shapes.items():
+        t = layer_tensors(m, q, 0, names[0], i, o, device, dtype)
+        x = torch.randn(1, i, device=device).to(dtype)
+        args = (t["indices"], t["centroids"].view(1, -1, v), None,
+                None if t["res_centroids"] is None else t["res_centroids"].view(1, -1, v), None, None,
+                t["perm"], t["weight_scale"], t["weight_bias"], None, i, o)
+        y = ref.quant_gemv(x, *args)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(7):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ref.quant_gemv(x, *args); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = sorted(ts)[len(ts) // 2]
+        for n in names:
+            out["us_per_shape"][n] = round(us, 2)
+            per_layer_us += us
+        if prefill_tokens and (i, o) == (m["hidden"], m["hidden"]):
+            # the reference's prefill path on this shape: dequant kernel + cuBLAS (vptq/ops/quant_gemm.py:231-275)
+            inv = torch.argsort(t["perm"].view(torch.uint16).to(torch.int64)).to(torch.uint16).view(torch.int16)
+            dargs = (t["indices"], t["centroids"].view(1, -1, v), None,
+                     None if t["res_centroids"] is None else t["res_centroids"].view(1, -1, v), None, None, inv,
+                     t["weight_scale"], t["weight_bias"], v, i, o)
+            xp = torch.randn(prefill_tokens, i, device=device).to(dtype)
+            W = ref.dequant(*dargs)
+            torch.nn.functional.linear(xp, W)
+            torch.cuda.synchronize()
+            tp_ = []
+            for _ in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); W = ref.dequant(*dargs); yy = torch.nn.functional.linear(xp, W); e1.record()
+                torch.cuda.synchronize()
+                tp_.append(e0.elapsed_time(e1))
+            prefill = {"shape": f"{o}x{i}", "tokens": prefill_tokens, "ms": round(sorted(tp_)[len(tp_) // 2], 4)}
+        del t
+    out["tokens_per_s"] = round(1e6 / (per_layer_us * m["layers"]), 2)
+    if prefill:
+        out["prefill_dequant_plus_cublas"] = prefill
+    return out
 
 
 def main():
@@ -508,11 +687,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--tp-mode", default="p2p", choices=["p2p", "nccl"],
                     help="N > 1: exchange fused into the GEMV over peer memory (p2p) or memset + NCCL all-reduce (nccl)")
     ap.add_argument("--tp-eager", action="store_true", help="N > 1: launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--debug-layers", type=int, default=0, help="debugging only: truncate the model (invalid as a result)")
+    ap.add_argument("--model", default="llama3-8b", choices=sorted(MODELS))
+    ap.add_argument("--no-check", action="store_true", help="skip the unsharded recomputation of the token")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

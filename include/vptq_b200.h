@@ -214,7 +214,10 @@ VPTQ_B200_API int vptq_b200_quant_gemv_multi_ws(int32_t n, const vptq_linear_des
  * publishes this launch's epoch in every peer's flag array; a launch with wait_slot >= 0 polls
  * the flags of the launch that produced its x before reading it.  All ranks must issue the same
  * sequence of launches; `slot` identifies a launch position within one token (static under CUDA
- * graphs: the epochs live in device memory).  No reference counterpart.
+ * graphs: the epochs live in device memory).  `workspace` as for vptq_b200_quant_gemv_multi_ws (may be NULL:
+ * layers carrying index lists then run the generic kernel).  A flag wait that does not complete within ~2 s
+ * sets *error (the outputs of that token are then undefined; later waits return at once): the host must check
+ * it.  No reference counterpart.
  */
 #define VPTQ_MAX_FUSED 4
 #define VPTQ_MAX_RANKS 8
@@ -232,8 +235,8 @@ typedef struct vptq_tp_exchange {
 
 VPTQ_B200_API int vptq_b200_quant_gemv_multi_tp(int32_t n, const vptq_linear_desc* const* descs, const void* x,
                                                 int64_t x_stride, void* const* ys, const int64_t* y_strides,
-                                                int32_t tokens, const vptq_tp_exchange* tp, uint32_t flags,
-                                                void* stream);
+                                                int32_t tokens, const vptq_tp_exchange* tp, void* workspace,
+                                                size_t workspace_bytes, uint32_t flags, void* stream);
 
 /*
  * W[o][f] (row-major [O][I], `dtype`), scale/bias/perm applied -- what the reference's dequant

@@ -225,7 +225,8 @@ int vptq_b200_quant_gemv_multi_ws(int32_t n, const vptq_linear_desc* const* desc
 
 int vptq_b200_quant_gemv_multi_tp(int32_t n, const vptq_linear_desc* const* descs, const void* x, int64_t x_stride,
                                   void* const* ys, const int64_t* y_strides, int32_t tokens,
-                                  const vptq_tp_exchange* tp, uint32_t flags, void* stream) {
+                                  const vptq_tp_exchange* tp, void* workspace, size_t workspace_bytes, uint32_t flags,
+                                  void* stream) {
   if (!descs || !x || !ys || !y_strides || n < 1 || !tp) {
     set_error("quant_gemv_multi_tp: NULL argument");
     return VPTQ_ERR_INVALID;
@@ -248,7 +249,8 @@ int vptq_b200_quant_gemv_multi_tp(int32_t n, const vptq_linear_desc* const* desc
         return VPTQ_ERR_INVALID;
       }
   }
-  return gemv_multi_launch(n, descs, x, x_stride, ys, y_strides, tokens, flags, static_cast<cudaStream_t>(stream), tp);
+  return gemv_multi_launch(n, descs, x, x_stride, ys, y_strides, tokens, flags, static_cast<cudaStream_t>(stream), tp,
+                           workspace, workspace_bytes);
 }
 
 int vptq_b200_dequant(const vptq_linear_desc* desc, void* w_out, void* workspace, size_t workspace_bytes,

@@ -395,11 +395,11 @@ int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x
     set_error("gemv_multi: 1..%d layers and 1..2 tokens (got %d layers, %d tokens)", kMaxFused, n, tokens);
     return VPTQ_ERR_UNSUPPORTED;
   }
-  if (tokens == 1 && !(tp && tp->world > 1) && gemv_tune_lists() != 0 && workspace) {
+  if (tokens == 1 && gemv_tune_lists() != 0 && workspace) {
     bool all = true;
     for (int l = 0; l < n; ++l) all = all && gemv_lists_eligible(*descs[l]);
     if (all) {
-      const int rc = gemv_lists_launch(n, descs, x, ys, flags, stream, workspace, workspace_bytes);
+      const int rc = gemv_lists_launch(n, descs, x, ys, flags, stream, workspace, workspace_bytes, tp);
       if (rc != VPTQ_ERR_UNSUPPORTED && rc != VPTQ_ERR_WORKSPACE) return rc;
     }
   }

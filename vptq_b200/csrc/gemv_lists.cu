@@ -78,6 +78,16 @@ struct ListsParams {
   uint32_t off_bars, off_tab, off_red, off_piece, off_done, off_slice, off_res, off_x, off_ring;
   int stages;
   unsigned long long* prof;  // developer aid: %globaltimer stamps of the first / last CTA (or nullptr)
+  // tensor-parallel exchange over peer memory (tp_world <= 1: off), same protocol as the generic kernel
+  // (gemv_kernel.cuh): every output row is stored locally and into all peers' buffers, the last CTA of the
+  // launch publishes the launch's epoch in every peer's flag array, a launch with tp_wait_slot >= 0 polls the
+  // flags of the launch that produced its x before reading it
+  int tp_world, tp_rank, tp_slot, tp_wait_slot;
+  void* tp_peer_y[kMaxFusedLayers][8];  // [layer][rank]: start of THIS rank's slice in rank r's y
+  uint32_t* tp_peer_flags[8];           // rank r's flag array [slots][world]
+  uint32_t* tp_epoch;                   // local: completed runs per launch slot
+  uint32_t* tp_done;                    // local: CTA arrival counters per launch slot (zero at rest)
+  uint32_t* tp_error;                   // local: set when a flag wait timed out
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -302,6 +312,24 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   // -------- x arrives from the previous kernel.  Its (coalesced) loads are issued first and complete while
   // lane 0 of every warp queues the ring copies behind the slice copies in the TMA unit ---------------------
   pdl_wait_prior_grid();
+  if (mp.tp_world > 1 && mp.tp_wait_slot >= 0) {
+    // x is assembled from every rank's slice: wait until all peers have published the epoch of the launch
+    // that produces it (= this launch's own run number: both run once per token).  A wait that times out
+    // (~2 s) sets the error word, which the host checks; once it is set nobody waits any more.
+    if (tid < mp.tp_world && tid != mp.tp_rank) {
+      const uint32_t want = ld_volatile_u32(mp.tp_epoch + mp.tp_slot) + 1u;
+      const uint32_t* flag = mp.tp_peer_flags[mp.tp_rank] + mp.tp_wait_slot * mp.tp_world + tid;
+      const long long t0 = clock64();
+      while (ld_acquire_sys_u32(flag) < want) {
+        if (ld_volatile_u32(mp.tp_error) != 0u) break;
+        if (clock64() - t0 > (1ll << 32)) {
+          *mp.tp_error = 1u;
+          break;
+        }
+      }
+    }
+    __syncthreads();
+  }
   stamp(2);
   const T* x = reinterpret_cast<const T*>(mp.x);
   uint4 xa = make_uint4(0u, 0u, 0u, 0u), xb = xa;
@@ -528,38 +556,71 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   __syncthreads();
   stamp(8);
   const int nd = *s_ndone;
+  bool stored_to_peers = false;
   if (nd > 0) {
     // this CTA's arrival completed nd row blocks: every unit of their rows has added its sums
     __threadfence();
     const T* bias = reinterpret_cast<const T*>(L.bias);
     T* y = reinterpret_cast<T*>(L.y);
-    constexpr int kFB = 8;  // outputs per thread whose loads are in flight together
-    for (int i0 = tid; i0 < nd * kRB * 8; i0 += kFB * kLT) {
-      long long q[kFB];
-      int o[kFB];
+    // one thread per index row: 8 accumulators (64 bytes) in, one 16-byte vector of outputs out -- to this
+    // rank's y and, tensor-parallel, to the same place in every peer's buffer over NVLink
+    for (int i = tid; i < nd * kRB; i += kLT) {
+      const int r = s_done[i / kRB] * kRB + i % kRB;
+      if (r < Ro) {
+        unsigned long long* p = L.yacc + size_t(r) * 8;
+        long long q[8];
 #pragma unroll
-      for (int k = 0; k < kFB; ++k) {
-        const int i = i0 + k * kLT;
-        o[k] = -1;
-        q[k] = 0;
-        if (i < nd * kRB * 8) {
-          const int b = s_done[i / (kRB * 8)], rr = i % (kRB * 8);
-          const int r = b * kRB + (rr >> 3);
-          if (r < Ro) {
-            o[k] = r * 8 + (rr & 7);
-            asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(q[k]) : "l"(L.yacc + o[k]) : "memory");
+        for (int k = 0; k < 4; ++k)
+          asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(q[2 * k]), "=l"(q[2 * k + 1]) : "l"(p + 2 * k) : "memory");
+#pragma unroll
+        for (int k = 0; k < 4; ++k) *reinterpret_cast<ulonglong2*>(p + 2 * k) = make_ulonglong2(0ull, 0ull);  // zero at rest
+        const int o = r * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          v[e] = float(q[e]) * kFixInv + ((bias && o + e < L.O) ? DT<T>::to_float(bias[o + e]) : 0.f);
+        if (o + 8 <= L.O && (reinterpret_cast<uintptr_t>(y) & 15u) == 0) {
+          const uint4 pk = make_uint4(DT<T>::pack2(v[0], v[1]), DT<T>::pack2(v[2], v[3]), DT<T>::pack2(v[4], v[5]),
+                                      DT<T>::pack2(v[6], v[7]));
+          *reinterpret_cast<uint4*>(y + o) = pk;
+          if (mp.tp_world > 1) {
+            for (int rk = 0; rk < mp.tp_world; ++rk)
+              if (rk != mp.tp_rank) *reinterpret_cast<uint4*>(reinterpret_cast<T*>(mp.tp_peer_y[l][rk]) + o) = pk;
+            stored_to_peers = true;
           }
-        }
-      }
+        } else {
 #pragma unroll
-      for (int k = 0; k < kFB; ++k) {
-        if (o[k] >= 0) {
-          L.yacc[o[k]] = 0ull;  // zero at rest for the next launch
-          if (o[k] < L.O) y[o[k]] = DT<T>::from_float(float(q[k]) * kFixInv + (bias ? DT<T>::to_float(bias[o[k]]) : 0.f));
+          for (int e = 0; e < 8; ++e) {
+            if (o + e < L.O) {
+              const T hv = DT<T>::from_float(v[e]);
+              y[o + e] = hv;
+              if (mp.tp_world > 1) {
+                for (int rk = 0; rk < mp.tp_world; ++rk)
+                  if (rk != mp.tp_rank) reinterpret_cast<T*>(mp.tp_peer_y[l][rk])[o + e] = hv;
+                stored_to_peers = true;
+              }
+            }
+          }
         }
       }
     }
     if (tid < nd) L.counters[s_done[tid]] = 0u;  // leave the counters zeroed for the next launch
+  }
+  // -------- tensor-parallel hand-off: the last CTA of the launch publishes its epoch on every peer ----------
+  if (mp.tp_world > 1) {
+    if (stored_to_peers) __threadfence_system();  // this thread's peer stores are visible system-wide
+    __syncthreads();
+    if (tid == 0) {
+      const uint32_t prev = atomicAdd(mp.tp_done + mp.tp_slot, 1u);
+      if (prev == gridDim.x - 1u) {  // the whole launch (all fused layers) has stored its outputs
+        mp.tp_done[mp.tp_slot] = 0u;
+        const uint32_t e = ld_volatile_u32(mp.tp_epoch + mp.tp_slot) + 1u;
+        mp.tp_epoch[mp.tp_slot] = e;
+        __threadfence_system();
+        for (int r = 0; r < mp.tp_world; ++r)
+          if (r != mp.tp_rank) st_release_sys_u32(mp.tp_peer_flags[r] + mp.tp_slot * mp.tp_world + mp.tp_rank, e);
+      }
+    }
   }
   stamp(9);
 }
@@ -602,7 +663,7 @@ size_t gemv_lists_workspace_bytes(const vptq_linear_desc& d) {
 }
 
 int gemv_lists_launch(int n, const vptq_linear_desc* const* descs, const void* x, void* const* ys, uint32_t flags,
-                      cudaStream_t stream, void* workspace, size_t workspace_bytes) {
+                      cudaStream_t stream, void* workspace, size_t workspace_bytes, const vptq_tp_exchange* tp) {
   const DeviceInfo* dev = device_info();
   if (!dev) return VPTQ_ERR_CUDA;
   if (n < 1 || n > kMaxFusedLayers) {
@@ -758,6 +819,13 @@ int gemv_lists_launch(int n, const vptq_linear_desc* const* descs, const void* x
     begin += uint32_t(share[l]);
   }
   for (int l = n; l <= kMaxFusedLayers; ++l) mp.grid_begin[l] = begin;
+  if (tp && tp->world > 1) {
+    mp.tp_world = tp->world, mp.tp_rank = tp->rank, mp.tp_slot = tp->slot, mp.tp_wait_slot = tp->wait_slot;
+    for (int l = 0; l < n; ++l)
+      for (int r = 0; r < tp->world; ++r) mp.tp_peer_y[l][r] = tp->peer_y[l][r];
+    for (int r = 0; r < tp->world; ++r) mp.tp_peer_flags[r] = tp->peer_flags[r];
+    mp.tp_epoch = tp->epoch, mp.tp_done = tp->done, mp.tp_error = tp->error;
+  }
 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(begin);

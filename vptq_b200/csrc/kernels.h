@@ -99,7 +99,7 @@ constexpr int kMaxFusedLayers = 4;
 bool gemv_lists_eligible(const vptq_linear_desc& d);
 // n layers reading the same x in one launch.  VPTQ_ERR_UNSUPPORTED / VPTQ_ERR_WORKSPACE: use the generic kernel.
 int gemv_lists_launch(int n, const vptq_linear_desc* const* descs, const void* x, void* const* ys, uint32_t flags,
-                      cudaStream_t stream, void* workspace, size_t workspace_bytes);
+                      cudaStream_t stream, void* workspace, size_t workspace_bytes, const vptq_tp_exchange* tp = nullptr);
 size_t gemv_lists_workspace_bytes(const vptq_linear_desc& d);  // 0 when the layer is not eligible
 
 // -------------------------------------------------------------------------------------------

@@ -102,7 +102,7 @@ def lib() -> ctypes.CDLL:
                                                     ctypes.POINTER(i64), i32, vp, sz, u32, vp]
         L.vptq_b200_quant_gemv_multi_ws.restype = ctypes.c_int
         L.vptq_b200_quant_gemv_multi_tp.argtypes = [i32, ctypes.POINTER(dp), vp, i64, ctypes.POINTER(vp),
-                                                    ctypes.POINTER(i64), i32, ctypes.POINTER(TpExchange), u32, vp]
+                                                    ctypes.POINTER(i64), i32, ctypes.POINTER(TpExchange), vp, sz, u32, vp]
         L.vptq_b200_quant_gemv_multi_tp.restype = ctypes.c_int
         L.vptq_b200_lists_build_host.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp, sz, vp, ctypes.POINTER(sz),
                                                  ctypes.POINTER(i32)]
@@ -294,13 +294,17 @@ class FusedGemvTP:
         self.desc_arr = (ctypes.POINTER(LinearDesc) * n)(*[ctypes.pointer(d) for d in descs])
         self.y_arr = (ctypes.c_void_p * n)(*[y.data_ptr() for y in ys])
         self.stride_arr = (ctypes.c_int64 * n)(*[y.stride(0) for y in ys])
+        self.ws_bytes = None
 
     def __call__(self, x2d: torch.Tensor, flags: int = 0) -> None:
         dev = x2d.device
         with torch.cuda.device(dev):
+            if self.ws_bytes is None:
+                self.ws_bytes = sum(workspace_bytes(d, x2d.shape[0], OP_GEMV) for d in self.descs)
+            ws = workspace(dev, self.ws_bytes)
             rc = lib().vptq_b200_quant_gemv_multi_tp(self.n, self.desc_arr, x2d.data_ptr(), x2d.stride(0), self.y_arr,
-                                                     self.stride_arr, x2d.shape[0], ctypes.byref(self.ex), flags,
-                                                     _stream(dev))
+                                                     self.stride_arr, x2d.shape[0], ctypes.byref(self.ex), ws.data_ptr(),
+                                                     ws.numel(), flags, _stream(dev))
         check(rc, "vptq_b200_quant_gemv_multi_tp")
 
 
