@@ -192,22 +192,33 @@ def make_step(m, stack, device, dtype, rank, world, flags, tp_mode="nccl"):
     import torch.distributed as dist
     from vptq_b200 import native
     h, kv, f = m["hidden"], m["kv"], m["ffn"]
-    p2p = world > 1 and tp_mode == "p2p"
+    p2p = world > 1 and tp_mode in ("p2p", "p2p-plain")
+    tagged = p2p and tp_mode != "p2p-plain"
     if p2p:
-        # activations live in a symmetric arena mapped into every rank: the GEMV stores its slice into
-        # all peers' buffers and publishes an epoch flag; consumers poll the flags (no NCCL on the path)
+        # activations live in a symmetric arena mapped into every rank: the GEMV stores its slice into all peers'
+        # buffers (no NCCL on the path).  Default wire format: tagged 8-byte words {2 values, tag} that the
+        # consumer re-reads until the tag is current (no fence, no flag); "p2p-plain": plain values + epoch flags
         from vptq_b200 import tp
         nslots = 4 * len(stack)
-        arena = tp.PeerArena((h + 2 * kv + h + 2 * f + 2 * h) * 2 + nslots * world * 4 + 8192, device)
-        qkv, off_qkv = arena.alloc((1, h + 2 * kv), dtype)
-        o_buf, off_o = arena.alloc((1, h), dtype)
-        gu, off_gu = arena.alloc((1, 2 * f), dtype)
-        hs0, off_h0 = arena.alloc((1, h), dtype)
-        hs1, off_h1 = arena.alloc((1, h), dtype)
+        wb = 4 if tagged else 2   # bytes per output in the exchanged buffers
+        arena = tp.PeerArena((h + 2 * kv + h + 2 * f + 2 * h) * wb + nslots * world * 4 + 8192, device)
+        bdt, mul = (torch.uint8, wb) if tagged else (dtype, 1)
+        qkv_x, off_qkv = arena.alloc((1, (h + 2 * kv) * mul), bdt)
+        o_x, off_o = arena.alloc((1, h * mul), bdt)
+        gu_x, off_gu = arena.alloc((1, 2 * f * mul), bdt)
+        hs0_x, off_h0 = arena.alloc((1, h * mul), bdt)
+        hs1_x, off_h1 = arena.alloc((1, h * mul), bdt)
         _, off_flags = arena.alloc((nslots, world), torch.int32)
         tp_epoch = torch.zeros(nslots, dtype=torch.int32, device=device)
         tp_done = torch.zeros(nslots, dtype=torch.int32, device=device)
         tp_error = torch.zeros(1, dtype=torch.int32, device=device)
+        if tagged:   # the kernels also leave the plain local slice in ordinary full-width buffers
+            qkv = torch.zeros(1, h + 2 * kv, device=device, dtype=dtype)
+            gu = torch.zeros(1, 2 * f, device=device, dtype=dtype)
+            o_buf = torch.zeros(1, h, device=device, dtype=dtype)
+            hs0, hs1 = (torch.zeros(1, h, device=device, dtype=dtype) for _ in range(2))
+        else:
+            qkv, o_buf, gu, hs0, hs1 = qkv_x, o_x, gu_x, hs0_x, hs1_x
     else:
         # q|k|v and gate|up live side by side so that one memset + one all-reduce serve a fused launch
         qkv = torch.zeros(1, h + 2 * kv, device=device, dtype=dtype)
@@ -258,15 +269,17 @@ def make_step(m, stack, device, dtype, rank, world, flags, tp_mode="nccl"):
 
     p2p_launch = []
     if p2p:
-        e2 = 2  # bytes per element
+        e2 = wb  # bytes per output in the exchanged buffers
         hs_off = [off_h0, off_h1]
+        hs_x = [hs0_x, hs1_x]
         for li, layer in enumerate(stack):
             cur = li % 2
 
             def ex(slot_in_layer, wait, y_offsets, names, layer=layer, li=li):
                 return tp.make_exchange(arena, slot=4 * li + slot_in_layer, wait_slot=wait, y_offsets=y_offsets,
                                         slice_bytes=[rank * layer[n]["out_loc"] * e2 for n in names],
-                                        flags_offset=off_flags, epoch=tp_epoch, done=tp_done, error=tp_error)
+                                        flags_offset=off_flags, epoch=tp_epoch, done=tp_done, error=tp_error,
+                                        fmt=native.TP_TAGGED if tagged else native.TP_PLAIN, num_slots=nslots)
 
             def fz(names, ys_full, exch, layer=layer):
                 return native.FusedGemvTP([layer[n]["desc"] for n in names],
@@ -280,17 +293,24 @@ def make_step(m, stack, device, dtype, rank, world, flags, tp_mode="nccl"):
                 fz(("gate", "up"), (buf["gate"], buf["up"]), ex(2, 4 * li + 1, [off_gu, off_gu + f * e2], ("gate", "up"))),
                 fz(("down",), (hs[cur],), ex(3, 4 * li + 2, [hs_off[cur]], ("down",)))))
 
+    h_plain = torch.zeros(1, h, device=device, dtype=dtype) if tagged else None
+
     def step():
         launches[0] = 0
         x, cur = x_in, 0
         if p2p:
+            # (tagged: a consumer's x is its local tagged buffer; the q / gate part starts at offset 0 of qkv / gu)
+            xq, xo, xg = (qkv_x, o_x, gu_x) if tagged else (buf["q"], buf["o"], buf["gate"])
             for f_qkv, f_o, f_gu, f_down in p2p_launch:
                 f_qkv(x, flags)
-                f_o(buf["q"], flags)
-                f_gu(buf["o"], flags)
-                f_down(buf["gate"], flags)
+                f_o(xq, flags)
+                f_gu(xo, flags)
+                f_down(xg, flags)
                 launches[0] += 4
-                x, cur = hs[cur], 1 - cur
+                x, cur = (hs_x[cur] if tagged else hs[cur]), 1 - cur
+            if tagged:   # the last hidden state, every rank's slice, back to plain 16-bit values
+                h_plain.copy_(tp.untag(x, dtype))
+                return h_plain
             return x
         for li, layer in enumerate(stack):
             if fuse:
@@ -349,12 +369,12 @@ def run_ours(args):
     torch.manual_seed(4321)
     x_host = torch.randn(1, m["hidden"]).to(dtype).pin_memory()
     tp_fallback = None
-    if tp_mode == "p2p":
+    if tp_mode in ("p2p", "p2p-plain"):
         # peer-mapped activations need symmetric memory, and the fused exchange must get through one eager
         # token without a refused launch or a flag time-out; every rank must take the same decision
         ok = torch.ones(1, device=device)
         try:
-            x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags, "p2p")
+            x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags, tp_mode)
             x_in.copy_(x_host, non_blocking=True)
             step()
             torch.cuda.synchronize()
@@ -368,7 +388,7 @@ def run_ours(args):
         if float(ok.item()) == 0.0:
             tp_mode, tp_fallback = "nccl", tp_fallback or "another rank could not set up the fused exchange"
             torch.cuda.synchronize()
-    if tp_mode != "p2p":
+    if tp_mode not in ("p2p", "p2p-plain"):
         x_in, step, launches = make_step(m, stack, device, dtype, rank, world, flags, tp_mode)
     y_host = torch.empty(1, m["hidden"], dtype=dtype).pin_memory()
 
@@ -494,13 +514,13 @@ def run_ours(args):
             "config": {"workload": workload_string(m, q, cfg_name),
                        "parallelism": (f"tp{world} (out_features sharded; " +
                                        ("exchange fused into the GEMV: NVLink peer stores + epoch flags, no NCCL call"
-                                        if tp_mode == "p2p" else "1 NCCL all-reduce per launch: q|k|v, o, gate|up, down") + ")")
+                                        if tp_mode.startswith("p2p") else "1 NCCL all-reduce per launch: q|k|v, o, gate|up, down") + ")")
                                       if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2: 2.6 GB of distinct packed indices streamed per step",
                        "fusion": "q+k+v and gate+up each in one launch (vptq_b200_quant_gemv_multi)" if
                                  not os.environ.get("BENCH_NO_FUSE") else "one launch per linear",
                        "launch": ("one CUDA graph per token" if use_graph else "eager launches") +
-                                 ", PDL " + ("off" if (args.no_pdl or (world > 1 and tp_mode != "p2p")) else "on")},
+                                 ", PDL " + ("off" if (args.no_pdl or (world > 1 and not tp_mode.startswith("p2p"))) else "on")},
             "gpu_launches": n_launch * args.steps,
             "e2e": {"value": round(1e3 / (ms_e2e / e2e_steps), 2), "unit": "tokens/s",
                     "h2d_bytes_per_step": x_host.numel() * 2, "d2h_bytes_per_step": y_host.numel() * 2,
@@ -689,8 +709,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
-    ap.add_argument("--tp-mode", default="p2p", choices=["p2p", "nccl"],
-                    help="N > 1: exchange fused into the GEMV over peer memory (p2p) or memset + NCCL all-reduce (nccl)")
+    ap.add_argument("--tp-mode", default="p2p", choices=["p2p", "p2p-plain", "nccl"],
+                    help="N > 1: exchange fused into the GEMV over peer memory (p2p: tagged words; p2p-plain: plain "
+                         "values + epoch flags) or memset + NCCL all-reduce (nccl)")
     ap.add_argument("--tp-eager", action="store_true", help="N > 1: launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--debug-layers", type=int, default=0, help="debugging only: truncate the model (invalid as a result)")
     ap.add_argument("--model", default="llama3-8b", choices=sorted(MODELS))

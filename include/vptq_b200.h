@@ -218,7 +218,21 @@ VPTQ_B200_API int vptq_b200_quant_gemv_multi_ws(int32_t n, const vptq_linear_des
  * layers carrying index lists then run the generic kernel).  A flag wait that does not complete within ~2 s
  * sets *error (the outputs of that token are then undefined; later waits return at once): the host must check
  * it.  No reference counterpart.
+ *
+ * Two wire formats (vptq_tp_exchange::format):
+ *   VPTQ_TP_PLAIN   16-bit outputs stored as they are + one epoch flag per (launch, source rank); the producer
+ *                   needs two system-scope fences per launch (data before flag), ~8 us per dependent launch.
+ *   VPTQ_TP_TAGGED  every pair of 16-bit outputs travels in one 8-byte word {2 values, 32-bit tag}, tag =
+ *                   run * num_slots + slot + 1 of the producing launch; an aligned 8-byte store is atomic, so the
+ *                   consumer simply re-reads a word until its tag is the one it expects: no fence, no flag, one
+ *                   NVLink one-way latency (the idea of NCCL's LL protocol).  peer_y[l][r] then points at THIS
+ *                   rank's slice inside rank r's TAGGED buffer (4 bytes per output; entry [rank] = the local
+ *                   one, also written), and a launch with wait_slot >= 0 takes `x` = its local tagged buffer
+ *                   (in_features / 2 words).  ys[l] still receives the plain local slice.  Only for launches
+ *                   whose layers all carry index lists (list kernel), one token, out_features % 8 == 0.
  */
+#define VPTQ_TP_PLAIN 0
+#define VPTQ_TP_TAGGED 1
 #define VPTQ_MAX_FUSED 4
 #define VPTQ_MAX_RANKS 8
 typedef struct vptq_tp_exchange {
@@ -231,6 +245,8 @@ typedef struct vptq_tp_exchange {
   uint32_t* epoch;   /* local uint32 [num_slots], zero-initialised once */
   uint32_t* done;    /* local uint32 [num_slots], zero-initialised once */
   uint32_t* error;   /* local uint32, set to 1 when a flag wait timed out (~2 s) */
+  int32_t format;    /* VPTQ_TP_PLAIN or VPTQ_TP_TAGGED */
+  int32_t num_slots; /* launches per token (tag arithmetic of VPTQ_TP_TAGGED) */
 } vptq_tp_exchange;
 
 VPTQ_B200_API int vptq_b200_quant_gemv_multi_tp(int32_t n, const vptq_linear_desc* const* descs, const void* x,

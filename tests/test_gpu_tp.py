@@ -116,6 +116,38 @@ def _worker_p2p(rank, world, port, q):
             b_star = vo.quant_gemm(a_got, LB)
             errs.append(float(np.abs(a_got.astype(np.float32) - a_star).max() / np.abs(a_star).max()))
             errs.append(float(np.abs(yB.float().cpu().numpy() - b_star).max() / np.abs(b_star).max()))
+        # ---- the tagged wire format (8-byte words {2 values, tag}: no flags, no fences): both layers on the list
+        # kernel, C reads the tagged buffer A wrote, 5 tokens so that tags advance and buffers are reused ----
+        LC = vo.make_layer(in_features=2048, out_features=1024, vector_len=8, num_centroids=65536, num_res_centroids=256, seed=43)
+        shC = tp.shard_module(make_module(LC, f"cuda:{rank}"), rank, world).shard
+        shC(torch.zeros(0, LC.in_features, device=dev, dtype=torch.float16))
+        tA, toffA = arena.alloc((1, 2048 * 4), torch.uint8)
+        tC, toffC = arena.alloc((1, 1024 * 4), torch.uint8)
+        pA = torch.zeros(1, 2048, device=dev, dtype=torch.float16)
+        pC = torch.zeros(1, 1024, device=dev, dtype=torch.float16)
+        epoch2 = torch.zeros(2, dtype=torch.int32, device=dev)
+        done2 = torch.zeros(2, dtype=torch.int32, device=dev)
+        kw = dict(flags_offset=off_flags, epoch=epoch2, done=done2, error=error, fmt=native.TP_TAGGED, num_slots=2)
+        exA2 = tp.make_exchange(arena, slot=0, wait_slot=-1, y_offsets=[toffA], slice_bytes=[rank * locA * 4], **kw)
+        exC2 = tp.make_exchange(arena, slot=1, wait_slot=0, y_offsets=[toffC], slice_bytes=[rank * locB * 4], **kw)
+        gA = native.FusedGemvTP([shards[0]._desc_cache[0]], [pA[:, rank * locA:(rank + 1) * locA]], exA2)
+        gC = native.FusedGemvTP([shC._desc_cache[0]], [pC[:, rank * locB:(rank + 1) * locB]], exC2)
+        for it in range(5):
+            x_np = vo.make_x(1, 1024, "fp16", seed=200 + it)
+            gA(x_to_t(x_np, LA, f"cuda:{rank}"), native.FLAG_PDL)
+            gC(tA, native.FLAG_PDL)
+            torch.cuda.synchronize()
+            dist.barrier()
+            torch.cuda.synchronize()
+            a_got = tp.untag(tA, torch.float16).cpu().numpy()
+            c_got = tp.untag(tC, torch.float16).float().cpu().numpy()
+            a_star = vo.quant_gemm(x_np, LA)
+            c_star = vo.quant_gemm(a_got, LC)
+            errs.append(float(np.abs(a_got.astype(np.float32) - a_star).max() / np.abs(a_star).max()))
+            errs.append(float(np.abs(c_got - c_star).max() / np.abs(c_star).max()))
+            # the plain local slices the kernels also leave behind
+            sl = slice(rank * locB, (rank + 1) * locB)
+            assert torch.equal(pC[:, sl].cpu(), torch.from_numpy(c_got[:, sl]).half())
         q.put((rank, errs, int(error.item())))
     finally:
         dist.destroy_process_group()

@@ -403,6 +403,11 @@ int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x
       if (rc != VPTQ_ERR_UNSUPPORTED && rc != VPTQ_ERR_WORKSPACE) return rc;
     }
   }
+  if (tp && tp->world > 1 && tp->format == VPTQ_TP_TAGGED) {
+    set_error("gemv_multi: the tagged exchange format is implemented by the list kernel only (layers without index "
+              "lists, several tokens or no workspace: use VPTQ_TP_PLAIN)");
+    return VPTQ_ERR_UNSUPPORTED;
+  }
   const vptq_linear_desc& d0 = *descs[0];
   double vol[kMaxFused], total = 0;
   for (int l = 0; l < n; ++l) {

@@ -88,6 +88,7 @@ struct ListsParams {
   uint32_t* tp_epoch;                   // local: completed runs per launch slot
   uint32_t* tp_done;                    // local: CTA arrival counters per launch slot (zero at rest)
   uint32_t* tp_error;                   // local: set when a flag wait timed out
+  int tp_format, tp_nslots;             // VPTQ_TP_PLAIN / VPTQ_TP_TAGGED; launches per token (tag arithmetic)
 };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
@@ -154,6 +155,28 @@ __device__ __forceinline__ uint4 load8(const T* p, int f, int fend, uint16_t fil
   for (int k = 0; k < 8; ++k) h[k] = (f + k < fend) ? reinterpret_cast<const uint16_t*>(p)[f + k] : fill;
   return make_uint4(h[0] | uint32_t(h[1]) << 16, h[2] | uint32_t(h[3]) << 16, h[4] | uint32_t(h[5]) << 16,
                     h[6] | uint32_t(h[7]) << 16);
+}
+
+// VPTQ_TP_TAGGED: 8 consecutive activations = four 8-byte words {2 values, tag}, written by any rank with aligned
+// 16-byte stores (each 8-byte half lands atomically).  Re-read until all four tags are the expected one.
+__device__ __forceinline__ uint4 load8_tagged(const void* xl, int f, uint32_t tag, uint32_t* error) {
+  const uint8_t* p = reinterpret_cast<const uint8_t*>(xl) + size_t(f) * 4;
+  uint4 a, b;
+  const long long t0 = clock64();
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "l"(p) : "memory");
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+                 : "l"(p + 16)
+                 : "memory");
+    if (a.y == tag && a.w == tag && b.y == tag && b.w == tag) break;
+    if (ld_volatile_u32(error) != 0u) break;
+    if (clock64() - t0 > (1ll << 32)) {  // ~2 s: give up loudly instead of hanging the GPU
+      *error = 1u;
+      break;
+    }
+  }
+  return make_uint4(a.x, a.z, b.x, b.z);
 }
 
 // x' = x * scale for 8 features (stored as fp16) and sum x * wbias (fp32)
@@ -312,12 +335,17 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   // -------- x arrives from the previous kernel.  Its (coalesced) loads are issued first and complete while
   // lane 0 of every warp queues the ring copies behind the slice copies in the TMA unit ---------------------
   pdl_wait_prior_grid();
-  if (mp.tp_world > 1 && mp.tp_wait_slot >= 0) {
+  const bool tagged = mp.tp_world > 1 && mp.tp_format == VPTQ_TP_TAGGED;
+  // tag of the words this launch writes / expects in its x: run number * launches per token + slot + 1
+  const uint32_t run = mp.tp_world > 1 ? ld_volatile_u32(mp.tp_epoch + mp.tp_slot) : 0u;
+  const uint32_t tag_out = run * uint32_t(mp.tp_nslots) + uint32_t(mp.tp_slot) + 1u;
+  const uint32_t tag_in = run * uint32_t(mp.tp_nslots) + uint32_t(mp.tp_wait_slot) + 1u;
+  if (mp.tp_world > 1 && mp.tp_wait_slot >= 0 && !tagged) {
     // x is assembled from every rank's slice: wait until all peers have published the epoch of the launch
     // that produces it (= this launch's own run number: both run once per token).  A wait that times out
     // (~2 s) sets the error word, which the host checks; once it is set nobody waits any more.
     if (tid < mp.tp_world && tid != mp.tp_rank) {
-      const uint32_t want = ld_volatile_u32(mp.tp_epoch + mp.tp_slot) + 1u;
+      const uint32_t want = run + 1u;
       const uint32_t* flag = mp.tp_peer_flags[mp.tp_rank] + mp.tp_wait_slot * mp.tp_world + tid;
       const long long t0 = clock64();
       while (ld_acquire_sys_u32(flag) < want) {
@@ -333,8 +361,14 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   stamp(2);
   const T* x = reinterpret_cast<const T*>(mp.x);
   uint4 xa = make_uint4(0u, 0u, 0u, 0u), xb = xa;
-  if (colA) xa = load8<T>(x, fA, fAend, 0);
-  if (colB) xb = load8<T>(x, fB, fBend, 0);
+  if (tagged && mp.tp_wait_slot >= 0) {
+    // (in_features % 8 == 0 is checked on the host: whole 8-feature groups only)
+    if (colA) xa = load8_tagged(mp.x, fA, tag_in, mp.tp_error);
+    if (colB) xb = load8_tagged(mp.x, fB, tag_in, mp.tp_error);
+  } else {
+    if (colA) xa = load8<T>(x, fA, fAend, 0);
+    if (colB) xb = load8<T>(x, fB, fBend, 0);
+  }
   for (int qi = 0; qi < min(stages, nstage); ++qi) issue(qi, qi);
 
   if constexpr (RES) {
@@ -583,7 +617,18 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
           const uint4 pk = make_uint4(DT<T>::pack2(v[0], v[1]), DT<T>::pack2(v[2], v[3]), DT<T>::pack2(v[4], v[5]),
                                       DT<T>::pack2(v[6], v[7]));
           *reinterpret_cast<uint4*>(y + o) = pk;
-          if (mp.tp_world > 1) {
+          if (tagged) {
+            // two 16-byte stores of {pair, tag, pair, tag} into every rank's tagged buffer (the local one too)
+            for (int rk = 0; rk < mp.tp_world; ++rk) {
+              uint8_t* dst = reinterpret_cast<uint8_t*>(mp.tp_peer_y[l][rk]) + size_t(o) * 4;
+              asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "r"(pk.x), "r"(tag_out), "r"(pk.y),
+                           "r"(tag_out)
+                           : "memory");
+              asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 16), "r"(pk.z), "r"(tag_out),
+                           "r"(pk.w), "r"(tag_out)
+                           : "memory");
+            }
+          } else if (mp.tp_world > 1) {
             for (int rk = 0; rk < mp.tp_world; ++rk)
               if (rk != mp.tp_rank) *reinterpret_cast<uint4*>(reinterpret_cast<T*>(mp.tp_peer_y[l][rk]) + o) = pk;
             stored_to_peers = true;
@@ -594,7 +639,7 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
             if (o + e < L.O) {
               const T hv = DT<T>::from_float(v[e]);
               y[o + e] = hv;
-              if (mp.tp_world > 1) {
+              if (mp.tp_world > 1 && !tagged) {
                 for (int rk = 0; rk < mp.tp_world; ++rk)
                   if (rk != mp.tp_rank) reinterpret_cast<T*>(mp.tp_peer_y[l][rk])[o + e] = hv;
                 stored_to_peers = true;
@@ -614,11 +659,12 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
       const uint32_t prev = atomicAdd(mp.tp_done + mp.tp_slot, 1u);
       if (prev == gridDim.x - 1u) {  // the whole launch (all fused layers) has stored its outputs
         mp.tp_done[mp.tp_slot] = 0u;
-        const uint32_t e = ld_volatile_u32(mp.tp_epoch + mp.tp_slot) + 1u;
-        mp.tp_epoch[mp.tp_slot] = e;
-        __threadfence_system();
-        for (int r = 0; r < mp.tp_world; ++r)
-          if (r != mp.tp_rank) st_release_sys_u32(mp.tp_peer_flags[r] + mp.tp_slot * mp.tp_world + mp.tp_rank, e);
+        mp.tp_epoch[mp.tp_slot] = run + 1u;  // (every CTA read `run` at its start)
+        if (!tagged) {
+          __threadfence_system();
+          for (int r = 0; r < mp.tp_world; ++r)
+            if (r != mp.tp_rank) st_release_sys_u32(mp.tp_peer_flags[r] + mp.tp_slot * mp.tp_world + mp.tp_rank, run + 1u);
+        }
       }
     }
   }
@@ -825,6 +871,15 @@ int gemv_lists_launch(int n, const vptq_linear_desc* const* descs, const void* x
       for (int r = 0; r < tp->world; ++r) mp.tp_peer_y[l][r] = tp->peer_y[l][r];
     for (int r = 0; r < tp->world; ++r) mp.tp_peer_flags[r] = tp->peer_flags[r];
     mp.tp_epoch = tp->epoch, mp.tp_done = tp->done, mp.tp_error = tp->error;
+    mp.tp_format = tp->format, mp.tp_nslots = tp->num_slots;
+    if (tp->format == VPTQ_TP_TAGGED) {
+      bool ok = tp->num_slots > tp->slot && (I % 8) == 0;
+      for (int l = 0; l < n; ++l) ok = ok && (descs[l]->out_features % 8) == 0 && tp->peer_y[l][tp->rank] != nullptr;
+      if (!ok) {
+        set_error("gemv_lists: VPTQ_TP_TAGGED needs in/out_features %% 8 == 0, num_slots > slot and a local tagged buffer");
+        return VPTQ_ERR_INVALID;
+      }
+    }
   }
 
   cudaLaunchConfig_t cfg{};

@@ -22,6 +22,7 @@ LIB_PATH = os.path.join(_HERE, "libvptq_b200.so")
 VPTQ_FP16, VPTQ_BF16 = 0, 1
 OP_GEMV, OP_DEQUANT, OP_GEMM, OP_GEMV_V2 = 0, 1, 2, 3
 FLAG_PDL = 1
+TP_PLAIN, TP_TAGGED = 0, 1
 ABI_VERSION = 5
 LISTS_DEFAULT = "1"   # VPTQ_B200_LISTS when unset
 
@@ -42,6 +43,7 @@ class TpExchange(ctypes.Structure):
         ("slot", ctypes.c_int32), ("wait_slot", ctypes.c_int32),
         ("peer_y", (ctypes.c_void_p * MAX_RANKS) * MAX_FUSED), ("peer_flags", ctypes.c_void_p * MAX_RANKS),
         ("epoch", ctypes.c_void_p), ("done", ctypes.c_void_p), ("error", ctypes.c_void_p),
+        ("format", ctypes.c_int32), ("num_slots", ctypes.c_int32),
     ]
 
 

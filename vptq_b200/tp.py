@@ -181,9 +181,10 @@ class PeerArena:
 
 
 def make_exchange(arena: PeerArena, *, slot: int, wait_slot: int, y_offsets, slice_bytes, flags_offset: int,
-                  epoch: torch.Tensor, done: torch.Tensor, error: torch.Tensor):
+                  epoch: torch.Tensor, done: torch.Tensor, error: torch.Tensor, fmt: int = 0, num_slots: int = 0):
     """Fill a vptq_tp_exchange for one launch: y_offsets[l] = byte offset (in the arena) of layer l's FULL-width
-    output buffer, slice_bytes[l] = byte offset of this rank's slice inside it."""
+    output buffer, slice_bytes[l] = byte offset of this rank's slice inside it.  fmt = native.TP_TAGGED: the
+    buffers are tagged-word buffers (4 bytes per output, include/vptq_b200.h) and num_slots = launches per token."""
     from . import native
     ex = native.TpExchange()
     import ctypes
@@ -195,4 +196,10 @@ def make_exchange(arena: PeerArena, *, slot: int, wait_slot: int, y_offsets, sli
     for r in range(arena.world):
         ex.peer_flags[r] = arena.peer_ptr(r, flags_offset)
     ex.epoch, ex.done, ex.error = epoch.data_ptr(), done.data_ptr(), error.data_ptr()
+    ex.format, ex.num_slots = int(fmt), int(num_slots)
     return ex
+
+
+def untag(buf: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Tagged-word buffer (uint8 view, 8 bytes per pair of outputs) -> the plain 16-bit values."""
+    return buf.view(torch.int32).view(-1, 2)[:, 0].contiguous().view(dtype).view(1, -1)
