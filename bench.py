@@ -163,7 +163,7 @@ def build_stack(m, q, device, rank, world, dtype):
     return stack
 
 
-def reference_hidden(m, q, device, dtype, x_in):
+def reference_hidden(m, q, device, dtype, x_in, lists=None):
     """The same token through the UNSHARDED layers on this GPU alone (one decoder layer resident at a time):
     what the tensor-parallel exchange must reproduce.  Same kernels, same chain as make_step."""
     import torch
@@ -176,7 +176,7 @@ def reference_hidden(m, q, device, dtype, x_in):
         out["x"] = x
         for name, i, o in model_linears(m):
             t = layer_tensors(m, q, li, name, i, o, device, dtype)
-            d = make_layer_desc(q, t, i, o, dtype)
+            d = make_layer_desc(q, t, i, o, dtype, lists=lists)
             y = torch.empty(1, o, device=device, dtype=dtype)
             native.quant_gemv(d, out[src[name]], y)
             torch.cuda.synchronize()
@@ -478,14 +478,14 @@ def run_ours(args):
         with torch.cuda.stream(s):
             x_chk = torch.empty(1, m["hidden"], device=device, dtype=dtype)
             x_chk.copy_(x_host)
-            if world == 1:
-                os.environ["VPTQ_B200_LISTS"] = "0" if os.environ.get("VPTQ_B200_LISTS", "1") != "0" else "1"
-            h_ref = reference_hidden(m, q, device, dtype, x_chk).float()
+            # the reference runs the OTHER decode kernel (generic when the measured path used the lists and vice
+            # versa): an independent implementation, and no list building for the unsharded layers
+            h_ref = reference_hidden(m, q, device, dtype, x_chk, lists=not lists_on).float()
             s.synchronize()
         err = float((h_final.float() - h_ref).abs().max() / h_ref.abs().max())
         # 4 * layers chained 16-bit roundings: the bar is loose, a wrong or stale slice misses it by orders of magnitude
         check = {"max_rel_err": round(err, 6), "ok": bool(err <= 2e-2), "against":
-                 "unsharded layers on rank 0" if world > 1 else "the other decode kernel (generic <-> lists), same token"}
+                 ("unsharded layers on rank 0, " if world > 1 else "") + "the other decode kernel (generic <-> lists), same token"}
     if world > 1:
         dist.barrier()
 
