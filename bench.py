@@ -308,8 +308,8 @@ def make_step(m, stack, device, dtype, rank, world, flags, tp_mode="nccl"):
                 f_down(xg, flags)
                 launches[0] += 4
                 x, cur = (hs_x[cur] if tagged else hs[cur]), 1 - cur
-            if tagged:   # the last hidden state, every rank's slice, back to plain 16-bit values
-                h_plain.copy_(tp.untag(x, dtype))
+            if tagged:   # the last hidden state, every rank's slice (waits for their tags), as plain 16-bit values
+                native.tp_untag(x, h_plain, p2p_launch[-1][3].ex)
                 return h_plain
             return x
         for li, layer in enumerate(stack):

@@ -255,6 +255,14 @@ VPTQ_B200_API int vptq_b200_quant_gemv_multi_tp(int32_t n, const vptq_linear_des
                                                 size_t workspace_bytes, uint32_t flags, void* stream);
 
 /*
+ * VPTQ_TP_TAGGED only: copy the full-width output of the launch described by `tp` (its exchange struct) from this
+ * rank's tagged buffer (n outputs, 4 bytes each) into plain 16-bit values y[n], waiting until every rank's words
+ * of that launch's latest run have arrived.  Enqueue it behind the producing launch on the same stream: this is
+ * how the LAST activation of a tensor-parallel chain (which no tagged consumer reads) becomes an ordinary tensor.
+ */
+VPTQ_B200_API int vptq_b200_tp_untag(const void* tagged, void* y, int32_t n, const vptq_tp_exchange* tp, void* stream);
+
+/*
  * W[o][f] (row-major [O][I], `dtype`), scale/bias/perm applied -- what the reference's dequant
  * returns (csrc/dequant.cu:227-287, Return_OUF_x_INF=true; python spec
  * vptq/ops/quant_gemm.py:43-158).

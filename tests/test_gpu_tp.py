@@ -136,11 +136,16 @@ def _worker_p2p(rank, world, port, q):
             x_np = vo.make_x(1, 1024, "fp16", seed=200 + it)
             gA(x_to_t(x_np, LA, f"cuda:{rank}"), native.FLAG_PDL)
             gC(tA, native.FLAG_PDL)
+            # the chain's last activation has no tagged consumer: vptq_b200_tp_untag waits for every rank's words
+            c_full = torch.zeros(1, 1024, device=dev, dtype=torch.float16)
+            native.tp_untag(tC, c_full, exC2)
             torch.cuda.synchronize()
+            c_early = c_full.float().cpu().numpy()
             dist.barrier()
             torch.cuda.synchronize()
             a_got = tp.untag(tA, torch.float16).cpu().numpy()
             c_got = tp.untag(tC, torch.float16).float().cpu().numpy()
+            assert np.array_equal(c_early, c_got)
             a_star = vo.quant_gemm(x_np, LA)
             c_star = vo.quant_gemm(a_got, LC)
             errs.append(float(np.abs(a_got.astype(np.float32) - a_star).max() / np.abs(a_star).max()))

@@ -253,6 +253,16 @@ int vptq_b200_quant_gemv_multi_tp(int32_t n, const vptq_linear_desc* const* desc
                            workspace, workspace_bytes);
 }
 
+int vptq_b200_tp_untag(const void* tagged, void* y, int32_t n, const vptq_tp_exchange* tp, void* stream) {
+  if (!tagged || !y || !tp || n < 8 || (n % 8) || tp->struct_size != sizeof(vptq_tp_exchange) ||
+      tp->format != VPTQ_TP_TAGGED || !tp->epoch || !tp->error || tp->slot < 0 || tp->slot >= tp->num_slots ||
+      (reinterpret_cast<uintptr_t>(tagged) & 15u) || (reinterpret_cast<uintptr_t>(y) & 15u)) {
+    set_error("tp_untag: NULL / misaligned argument, n %% 8 != 0 or not the exchange of a VPTQ_TP_TAGGED launch");
+    return VPTQ_ERR_INVALID;
+  }
+  return tp_untag_launch(tagged, y, n, *tp, static_cast<cudaStream_t>(stream));
+}
+
 int vptq_b200_dequant(const vptq_linear_desc* desc, void* w_out, void* workspace, size_t workspace_bytes,
                       void* stream) {
   if (int rc = validate(desc, true)) return rc;

@@ -671,6 +671,16 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   stamp(9);
 }
 
+// Tagged-word buffer -> plain 16-bit values, waiting for every word of the producing launch's LAST run (its
+// epoch counter has already been advanced locally when this kernel runs behind it on the same stream).
+__global__ void tp_untag_kernel(const void* tagged, uint4* y, int n8, const uint32_t* epoch, int slot, int nslots,
+                                uint32_t* error) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const uint32_t tag = (ld_volatile_u32(epoch + slot) - 1u) * uint32_t(nslots) + uint32_t(slot) + 1u;
+  y[i] = load8_tagged(tagged, i * 8, tag, error);
+}
+
 using ListsKernelFn = void (*)(const ListsParams);
 
 template <typename T>
@@ -689,6 +699,18 @@ int lists_tcw(int I) {
 }
 
 }  // namespace
+
+int tp_untag_launch(const void* tagged, void* y, int n, const vptq_tp_exchange& tp, cudaStream_t stream) {
+  const int n8 = n / 8;
+  tp_untag_kernel<<<(n8 + 255) / 256, 256, 0, stream>>>(tagged, reinterpret_cast<uint4*>(y), n8, tp.epoch, tp.slot,
+                                                         tp.num_slots, tp.error);
+  const cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("tp_untag launch: %s", cudaGetErrorString(e));
+    return VPTQ_ERR_CUDA;
+  }
+  return 0;
+}
 
 bool gemv_lists_eligible(const vptq_linear_desc& d) {
   if (!d.lists_stream || !d.lists_tab) return false;

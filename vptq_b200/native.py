@@ -30,7 +30,7 @@ EXPORTS = (
     "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
     "vptq_b200_dequant", "vptq_b200_quant_gemm", "vptq_b200_quant_gemv_v2", "vptq_b200_linear_host",
     "vptq_b200_debug_phase_stamps", "vptq_b200_quant_gemv_multi", "vptq_b200_quant_gemv_multi_tp",
-    "vptq_b200_lists_build_host", "vptq_b200_quant_gemv_multi_ws",
+    "vptq_b200_lists_build_host", "vptq_b200_quant_gemv_multi_ws", "vptq_b200_tp_untag",
 )
 
 MAX_FUSED, MAX_RANKS = 4, 8
@@ -109,6 +109,8 @@ def lib() -> ctypes.CDLL:
         L.vptq_b200_lists_build_host.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp, sz, vp, ctypes.POINTER(sz),
                                                  ctypes.POINTER(i32)]
         L.vptq_b200_lists_build_host.restype = ctypes.c_int
+        L.vptq_b200_tp_untag.argtypes = [vp, vp, i32, ctypes.POINTER(TpExchange), vp]
+        L.vptq_b200_tp_untag.restype = ctypes.c_int
         L.vptq_b200_debug_phase_stamps.argtypes = [vp]
         L.vptq_b200_debug_phase_stamps.restype = None
         for f in ("vptq_b200_quant_gemv", "vptq_b200_quant_gemm", "vptq_b200_dequant", "vptq_b200_quant_gemv_v2",
@@ -308,6 +310,14 @@ class FusedGemvTP:
                                                      self.stride_arr, x2d.shape[0], ctypes.byref(self.ex), ws.data_ptr(),
                                                      ws.numel(), flags, _stream(dev))
         check(rc, "vptq_b200_quant_gemv_multi_tp")
+
+
+def tp_untag(tagged: torch.Tensor, y: torch.Tensor, exchange: TpExchange) -> None:
+    """vptq_b200_tp_untag: the full-width output of the (VPTQ_TP_TAGGED) launch `exchange` -> plain values in y."""
+    dev = y.device
+    with torch.cuda.device(dev):
+        rc = lib().vptq_b200_tp_untag(tagged.data_ptr(), y.data_ptr(), y.numel(), ctypes.byref(exchange), _stream(dev))
+    check(rc, "vptq_b200_tp_untag")
 
 
 def quant_gemm(desc: LinearDesc, x2d: torch.Tensor, y2d: torch.Tensor, flags: int = 0) -> None:
