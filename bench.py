@@ -147,8 +147,28 @@ def make_layer_desc(q, t, i, o_loc, dtype, lists=None):
         weight_bias=t["weight_bias"], bias=None, lists=lists)
 
 
+def make_module(q, t, i, o_loc, dtype, device):
+    """The drop-in module (vptq_b200.VQuantLinear, reference constructor signature) holding these tensors."""
+    import torch
+    from vptq_b200 import VQuantLinear
+    Kr = q["num_res_centroids"]
+    mod = VQuantLinear(i, o_loc, vector_lens=[-1, q["vector_len"]], num_centroids=[-1, q["num_centroids"]],
+                       num_res_centroids=[-1, Kr], group_num=1, group_size=i, outlier_size=0, indices_as_float=False,
+                       enable_norm=True, enable_perm=True, is_indice_packed=True, bias=False, device=device, dtype=dtype,
+                       enable_proxy_error=False)
+    with torch.no_grad():
+        mod.indices.data = t["indices"]
+        mod.centroids.weight.data = t["centroids"]
+        if Kr > 0:
+            mod.res_centroids.weight.data = t["res_centroids"]
+        mod.perm.data = t["perm"]
+        mod.weight_scale.data, mod.weight_bias.data = t["weight_scale"], t["weight_bias"]
+    return mod.eval().prepare(dtype)
+
+
 def build_stack(m, q, device, rank, world, dtype):
-    """This rank's out_features shard of every linear; returns layer dicts."""
+    """This rank's out_features shard of every linear, as VQuantLinear modules; the C-ABI legs of the bench use the
+    descriptors those modules built (one copy of the weights and of the load-time index lists)."""
     v = q["vector_len"]
     stack = []
     for li in range(m["layers"]):
@@ -156,11 +176,85 @@ def build_stack(m, q, device, rank, world, dtype):
         for name, i, o in model_linears(m):
             o_loc = o // world
             t = layer_tensors(m, q, li, name, i, o, device, dtype, rows=(rank * o_loc // v, (rank + 1) * o_loc // v))
-            t["desc"] = make_layer_desc(q, t, i, o_loc, dtype)
+            t["module"] = make_module(q, t, i, o_loc, dtype, device)
+            t["desc"] = t["module"]._desc_cache[0]
             t["in"], t["out"], t["out_loc"] = i, o, o_loc
             layer[name] = t
         stack.append(layer)
     return stack
+
+
+def module_level(m, stack, device, dtype, x_host, steps, warmup, lm_head_rows=128256):
+    """The same token through the MODULE API a Hugging Face model calls (VQuantLinear.forward per projection, in
+    HF's order), three ways: eager and unfused (what a stock integration does), vptq_b200.fuse(model) + one CUDA
+    graph per token + PDL, and the latter followed by the fp16 lm_head GEMV (cuBLAS through torch: not a VPTQ
+    layer) -- per-step H2D of x and D2H of the result inside the timed region."""
+    import torch
+    import torch.nn as nn
+    import vptq_b200
+
+    class Layer(nn.Module):
+        def __init__(self, d):
+            super().__init__()
+            for n in ("q", "k", "v", "o", "gate", "up", "down"):
+                setattr(self, n + "_proj", d[n]["module"])
+
+        def forward(self, x):
+            q, k, v = self.q_proj(x), self.k_proj(x), self.v_proj(x)      # (attention itself is not a VPTQ layer)
+            o = self.o_proj(q)
+            g, u = self.gate_proj(o), self.up_proj(o)
+            return self.down_proj(g)
+
+    model = nn.Sequential(*[Layer(d) for d in stack])
+    x_dev = torch.zeros(1, m["hidden"], device=device, dtype=dtype)
+    s = torch.cuda.Stream(device)
+    s.wait_stream(torch.cuda.current_stream())
+    out = {}
+
+    def timed(fn, result, n_steps, n_warm):
+        fn()
+        s.synchronize()
+        host = torch.empty_like(result(), device="cpu").pin_memory()
+        def one():
+            x_dev.copy_(x_host, non_blocking=True)
+            fn()
+            host.copy_(result(), non_blocking=True)
+            s.synchronize()
+        for _ in range(n_warm):
+            one()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(n_steps):
+            one()
+        e1.record(s)
+        s.synchronize()
+        return 1e3 / (e0.elapsed_time(e1) / n_steps)
+
+    with torch.cuda.stream(s), torch.no_grad():
+        holder = {}
+        def eager():
+            holder["y"] = model(x_dev)
+        out["eager_unfused_tokens_per_s"] = round(timed(eager, lambda: holder["y"], max(3, steps // 4), 2), 2)
+        vptq_b200.fuse(model, pdl=True, prepare=False)
+        model(x_dev); s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            y_graph = model(x_dev)
+        out["fused_graph_tokens_per_s"] = round(timed(g.replay, lambda: y_graph, steps, max(warmup, 3)), 2)
+        # + the fp16 lm_head (vocabulary 128256): 1.05 GB more per token, read by cuBLAS
+        w_head = torch.randn(lm_head_rows, m["hidden"], device=device, dtype=dtype) * 0.02
+        torch.matmul(y_graph, w_head.t()); s.synchronize()
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, stream=s):
+            logits = torch.matmul(model(x_dev), w_head.t())
+        out["fused_graph_plus_lm_head_tokens_per_s"] = round(timed(g2.replay, lambda: logits, steps, max(warmup, 3)), 2)
+        vptq_b200.unfuse(model)
+    out["how"] = ("VQuantLinear.forward per projection in HF order (q,k,v,o,gate,up,down), host x -> H2D -> layers -> D2H "
+                  "every step; eager_unfused = 7 eager module calls per layer; fused_graph = vptq_b200.fuse(model) + "
+                  "CUDA graph + PDL; lm_head = fp16 128256 x hidden GEMV through torch (cuBLAS)")
+    return out
+
+
 
 
 def reference_hidden(m, q, device, dtype, x_in, lists=None):
@@ -542,6 +636,11 @@ def run_ours(args):
                 line["config"]["tp_fallback_reason"] = tp_fallback
         else:
             line["check"] = check
+        if world == 1 and not args.no_module_level:
+            try:
+                line["module_api"] = module_level(m, stack, device, dtype, x_host, args.steps, args.warmup)
+            except Exception as e:  # noqa: BLE001
+                line["module_api"] = {"error": repr(e)[:300]}
         if world == 1 and not args.no_ref_cuda:
             try:
                 line["ref_cuda"] = ref_cuda_timing(m, q, device, dtype)
@@ -707,6 +806,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-module-level", action="store_true", help="skip the VQuantLinear.forward / fuse(model) timings")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
     ap.add_argument("--tp-mode", default="p2p", choices=["p2p", "p2p-plain", "nccl"],
