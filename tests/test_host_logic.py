@@ -3,6 +3,7 @@ argument validation (no GPU compute is attempted here)."""
 import ctypes
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -191,3 +192,91 @@ def test_c_abi_validation_and_workspace_without_gpu():
     if not torch.cuda.is_available():
         rc = L.vptq_b200_quant_gemv(ctypes.byref(_desc()), 0x1000, 4096, 0x2000, 4096, 1, None, 0, 0, None)
         assert rc < 0 and native.last_error()
+
+
+# ---------------------------------------------------------------- checkpoint compatibility
+def _manifest():
+    import json
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "state_dict_manifest.json")))
+
+
+@pytest.mark.parametrize("cfg", sorted(_manifest()))
+def test_state_dict_matches_reference_module_and_round_trips_through_safetensors(cfg, tmp_path):
+    """Key names, shapes and storage dtypes of the REFERENCE module's state_dict (manifest generated from
+    /root/reference/vptq/layers/vqlinear.py by oracle/make_state_manifest.py), and a safetensors save / load of ours
+    (the format the public checkpoints ship in; uint16 payloads travel behind int16 views)."""
+    from safetensors.torch import load_file, save_file
+    from vptq_b200 import VQuantLinear
+    ent = _manifest()[cfg]
+    m = VQuantLinear(**ent["kwargs"], dtype=torch.float16, device="cpu", enable_proxy_error=False)
+    ours = {k: [list(v.shape), str(v.dtype)] for k, v in m.state_dict().items()}
+    assert ours == ent["state"]
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        for p in m.state_dict().values():
+            if p.dtype.is_floating_point:
+                p.copy_(torch.randn(p.shape, generator=g).to(p.dtype))
+            else:
+                info = torch.iinfo(p.dtype)
+                p.copy_(torch.randint(info.min, info.max, p.shape, generator=g, dtype=torch.int64).to(p.dtype))
+    path = str(tmp_path / "layer.safetensors")
+    save_file({k: v.contiguous() for k, v in m.state_dict().items()}, path)
+    m2 = VQuantLinear(**ent["kwargs"], dtype=torch.float16, device="cpu", enable_proxy_error=False)
+    res = m2.load_state_dict(load_file(path), strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert a.dtype == b.dtype and torch.equal(a, b), k
+    if ent["kwargs"]["enable_perm"] and ent["kwargs"]["is_indice_packed"]:
+        assert m2.perm.dtype == torch.int16          # uint16 feature indices behind an int16 view
+
+
+def test_reference_python_binds_our_library_through_the_stub():
+    """INTEGRATION.md option B: the REFERENCE's vptq/ops/quant_gemm.py, loaded from /root/reference with
+    integration/libvptq.py standing where its pybind module `vptq.libvptq` would be, takes the CUDA branch
+    (`__cuda_ops_installed`) and reaches libvptq_b200.so: a CPU tensor is refused by OUR argument check, not
+    silently computed by the reference's torch fallback.  (Authoring container only: the reference tree does not
+    travel to the GPU box.)"""
+    import importlib.util
+    import types
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shim
+    if not ref_shim.available():
+        pytest.skip("no reference tree here")
+    saved = {k: v for k, v in sys.modules.items() if k == "vptq" or k.startswith("vptq.")}
+    for k in saved:
+        del sys.modules[k]
+    try:
+        def load(name, path):
+            spec = importlib.util.spec_from_file_location(name, path)
+            m = importlib.util.module_from_spec(spec)
+            sys.modules[name] = m
+            spec.loader.exec_module(m)
+            return m
+        for pkg in ("vptq", "vptq.utils", "vptq.ops"):
+            sys.modules[pkg] = types.ModuleType(pkg)
+            sys.modules[pkg].__path__ = [os.path.join(ref_shim.REF, *pkg.split("."))]
+        for name in ("accelerate", "sentence_transformers"):
+            sys.modules.setdefault(name, types.ModuleType(name))
+        st = types.ModuleType("sentence_transformers.SentenceTransformer")
+        st.SentenceTransformer = type("SentenceTransformer", (), {})
+        sys.modules.setdefault("sentence_transformers.SentenceTransformer", st)
+        stub = load("vptq.libvptq", os.path.join(ROOT, "integration", "libvptq.py"))
+        sys.modules["vptq"].libvptq = stub
+        load("vptq.utils.pack", os.path.join(ref_shim.REF, "vptq/utils/pack.py"))
+        qg = load("vptq.ops.quant_gemm", os.path.join(ref_shim.REF, "vptq/ops/quant_gemm.py"))
+        assert qg.__dict__["__cuda_ops_installed"] is True and qg.vptq_ops is stub
+        L = vo.make_layer(in_features=256, out_features=64, vector_len=8, num_centroids=256, num_res_centroids=16, seed=3)
+        t = lambda a, dt: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).view(dt)
+        x = torch.zeros(1, 256, dtype=torch.float16)
+        with pytest.raises(RuntimeError, match="CUDA tensor"):
+            qg.quant_gemm(x, None, t(L.indices, torch.int32), t(L.centroids, torch.float16).view(1, -1), None, None, None,
+                          t(L.res_centroids, torch.float16).view(1, -1), t(L.perm, torch.int16),
+                          t(L.weight_scale, torch.float16), t(L.weight_bias, torch.float16), 8, -1, 1, 256, -1, 16, True,
+                          256, 0, 256, 64, 0, 0)
+    finally:
+        for k in [k for k in sys.modules if k == "vptq" or k.startswith("vptq.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+        for k in ("accelerate", "sentence_transformers", "sentence_transformers.SentenceTransformer"):
+            if isinstance(sys.modules.get(k), types.ModuleType) and not getattr(sys.modules[k], "__file__", None):
+                sys.modules.pop(k, None)

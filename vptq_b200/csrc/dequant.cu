@@ -325,14 +325,12 @@ int dequant_quant_order_launch(const vptq_linear_desc& d, void* wq_out, int64_t 
   const size_t smem = ((size_t(DQ_ROWS) * row_words * 4 + 127) & ~size_t(127)) + res_rep_bytes;
   dim3 grid(unsigned(d.num_codebooks * ((d.group_size + DQ_COLS - 1) / DQ_COLS)), unsigned((p.Ro + DQ_ROWS - 1) / DQ_ROWS));
   if (d.dtype == VPTQ_FP16) {
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(dequant_q8_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); });
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(dequant_q8_kernel<__half>), 100 * 1024)) return rc;
     dequant_q8_kernel<__half><<<grid, DQ_THREADS, smem, stream>>>(p);
     if (ld > d.in_features)
       dequant_zero_pad_kernel<__half><<<d.out_features, 64, 0, stream>>>(reinterpret_cast<__half*>(wq_out), ld, d.in_features, d.out_features);
   } else {
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(dequant_q8_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); });
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(dequant_q8_kernel<__nv_bfloat16>), 100 * 1024)) return rc;
     dequant_q8_kernel<__nv_bfloat16><<<grid, DQ_THREADS, smem, stream>>>(p);
     if (ld > d.in_features)
       dequant_zero_pad_kernel<__nv_bfloat16><<<d.out_features, 64, 0, stream>>>(reinterpret_cast<__nv_bfloat16*>(wq_out), ld, d.in_features, d.out_features);

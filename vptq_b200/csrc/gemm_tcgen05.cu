@@ -405,8 +405,6 @@ GemmWorkspace gemm_layout(const vptq_linear_desc& d, int tokens) {
   return w;
 }
 
-std::once_flag g_attr_once[2], g_prep_once;
-
 }  // namespace
 
 size_t gemm_workspace_bytes(const vptq_linear_desc& d, int tokens) { return gemm_layout(d, tokens).total; }
@@ -426,10 +424,10 @@ int gemm_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
 
   // 1. x' and rowbias
   const size_t prep_smem = align_up(size_t(d.in_features) * 2, 16);
-  std::call_once(g_prep_once, [] {
-    cudaFuncSetAttribute(prefill_prep_x<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
-    cudaFuncSetAttribute(prefill_prep_x<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 132 * 1024);
-  });
+  {
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(prefill_prep_x<__half>), 132 * 1024)) return rc;
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(prefill_prep_x<__nv_bfloat16>), 132 * 1024)) return rc;
+  }
   if (is_bf16)
     prefill_prep_x<__nv_bfloat16><<<tokens, 256, prep_smem, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(x), x_stride, d.perm,
@@ -456,14 +454,10 @@ int gemm_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
   dim3 grid(unsigned(std::min(ntiles, dev->sm_count)));  // persistent: one CTA per SM
   cudaError_t e;
   if (is_bf16) {
-    std::call_once(g_attr_once[1], [] {
-      cudaFuncSetAttribute(gemm_tn_tcgen05<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-    });
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(gemm_tn_tcgen05<__nv_bfloat16>), GEMM_SMEM)) return rc;
     gemm_tn_tcgen05<__nv_bfloat16><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(map_a, map_b, p);
   } else {
-    std::call_once(g_attr_once[0], [] {
-      cudaFuncSetAttribute(gemm_tn_tcgen05<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-    });
+    if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(gemm_tn_tcgen05<__half>), GEMM_SMEM)) return rc;
     gemm_tn_tcgen05<__half><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(map_a, map_b, p);
   }
   e = cudaGetLastError();

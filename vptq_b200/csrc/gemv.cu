@@ -5,6 +5,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <set>
 #include <unordered_set>
 #include <vector>
 
@@ -21,7 +22,7 @@ constexpr int kMaxClusterPartBytes = 16384;
 bool supported_vec_len(int v) { return v == 2 || v == 4 || v == 6 || v == 8 || v == 10 || v == 12 || v == 16; }
 
 std::mutex g_mutex;
-std::unordered_set<const void*> g_attr_done;
+std::set<std::pair<int, const void*>> g_attr_done;  // (device, kernel): the attribute is per device
 std::map<std::tuple<const void*, int, int, int>, int> g_max_clusters;
 
 // Developer tuning knobs (not part of the ABI): VPTQ_B200_GEMV_TUNE="rep=1,stages=2,seg=512,warps=16,cpg=4,wsplit=2,cluster=0,lists=0"
@@ -53,14 +54,18 @@ GemvKernelFn pick_kernel(const vptq_linear_desc& d, int nt, bool main_smem) {
 }  // namespace
 
 int ensure_smem_attr(const void* fn, int bytes) {
+  // cudaFuncSetAttribute applies to the CURRENT device only: a process that drives several GPUs (HF
+  // device_map="auto", pipeline splits) must opt in once per (device, kernel)
+  int dev = 0;
+  cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(g_mutex);
-  if (g_attr_done.count(fn)) return 0;
+  if (g_attr_done.count({dev, fn})) return 0;
   cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
   if (e != cudaSuccess) {
     set_error("cudaFuncSetAttribute(max dynamic smem=%d): %s", bytes, cudaGetErrorString(e));
     return VPTQ_ERR_CUDA;
   }
-  g_attr_done.insert(fn);
+  g_attr_done.insert({dev, fn});
   return 0;
 }
 
