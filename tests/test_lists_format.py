@@ -101,7 +101,7 @@ def test_structure(c):
 # ------------------------------------------------------------------------------------------------------
 # integer mirror of the kernel's partition arithmetic
 # ------------------------------------------------------------------------------------------------------
-def _kernel_partition(first, tail, Ro, Q, ncta, warps=16, sps=4, rb=32):
+def _kernel_partition(first, tail, Ro, Q, ncta, warps=16, sps=8, rb=32):
     """Walks every CTA / warp / stage exactly as gemv_lists_kernel does.  Returns (entries counted per unit,
     units written per writer kind, arrivals per row block)."""
     U = Q * Ro

@@ -47,8 +47,10 @@ constexpr int kSliceEntries = 4096;
 constexpr int kSliceBytes = kSliceEntries * 16;  // 64 KiB
 constexpr int kTileMax = 4096;
 constexpr int kLW = 16, kLT = kLW * 32;  // warps, threads per CTA
-constexpr int kSPS = 4;                  // steps (32 entries, 128 bytes each) per ring stage
-constexpr int kStageBytes = kSPS * 128;
+constexpr int kSPS = 4;                  // steps (32 entries, 128 bytes each) per batch: loads of 4 steps in flight
+constexpr int kBPS = 2;                  // batches per ring stage (one TMA copy / one barrier wait per 8 steps)
+constexpr int kStSteps = kSPS * kBPS;
+constexpr int kStageBytes = kStSteps * 128;
 constexpr int kMaxWindow = 3072;  // units of one CTA (bounds the tab window in shared memory)
 constexpr int kRB = 32;           // index rows per arrival counter
 constexpr int kResRep = 8;        // bank-group replication of the residual table
@@ -316,11 +318,11 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   const int TB = two ? int(s_tab[nA] & kStepMask) : T1;  // first step of segment B
   // the run as a sequence of ring stages; a stage never straddles the segment boundary
   const int e1 = min(t_end, TB), b2 = max(t_begin, TB);
-  const int n1 = (max(e1 - t_begin, 0) + kSPS - 1) / kSPS, n2 = (max(t_end - b2, 0) + kSPS - 1) / kSPS;
+  const int n1 = (max(e1 - t_begin, 0) + kStSteps - 1) / kStSteps, n2 = (max(t_end - b2, 0) + kStSteps - 1) / kStSteps;
   const int nstage = n1 + n2;
   auto stage_at = [&](int qi, int& t, int& cnt) {
-    if (qi < n1) t = t_begin + qi * kSPS, cnt = min(kSPS, e1 - t);
-    else t = b2 + (qi - n1) * kSPS, cnt = min(kSPS, t_end - t);
+    if (qi < n1) t = t_begin + qi * kStSteps, cnt = min(kStSteps, e1 - t);
+    else t = b2 + (qi - n1) * kStSteps, cnt = min(kStSteps, t_end - t);
   };
   // warp-collective: start the copy of stage qi of the run into ring slot `slot` (= qi mod stages)
   auto issue = [&](int qi, int slot) {
@@ -450,15 +452,14 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
     int slot = 0, qi = 0, t = 0;
     uint32_t par = 0;
     uint32_t slice_base = 0, x_base = 0;
-    // One ring stage = one batch of up to kSPS steps: all entry words, then all gathers, then the arithmetic.
+    // One batch = up to kSPS steps of a ring stage: all entry words, then all gathers, then the arithmetic.
     //   KEND = 0: no unit ends inside the batch (straight-line FMAs)
     //   KEND = k in 1..kSPS (full batches only): the current unit ends with the batch's k-th step and the next
     //             one does not end inside the batch -- the flush sits at a fixed place, no per-step test
     //   KEND < 0: generic (partial batches at the end of a run / segment, units shorter than a batch)
-    auto batch = [&](auto kend_tag, int cnt) {
+    auto batch = [&](auto kend_tag, int cnt, uint32_t st) {
       constexpr int KEND = decltype(kend_tag)::value;
       constexpr bool FULL = KEND >= 0;
-      const uint32_t st = ring_lane + uint32_t(slot) * uint32_t(kStageBytes);
       uint32_t ent[kSPS];
       uint32_t cw[kSPS][4], rw[kSPS][4];
       uint16_t xh[kSPS];
@@ -519,20 +520,24 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
       cb = part ? cbiasB : cbiasA;
 #pragma unroll 1
       for (int si = 0; si < np; ++si, ++qi) {
-        const int cnt = min(kSPS, pe - t);
         mbar_wait(&full[slot], par);
-        const int k = u_end - t;  // steps left in the current unit (>= 1)
-        if (cnt == kSPS && k > kSPS) {
-          batch(std::integral_constant<int, 0>{}, cnt);
-        } else if (cnt == kSPS && !(u + 1 < nun && int(s_tab[u + 2] & kStepMask) - t <= kSPS)) {
-          switch (k) {
-            case 1: batch(std::integral_constant<int, 1>{}, cnt); break;
-            case 2: batch(std::integral_constant<int, 2>{}, cnt); break;
-            case 3: batch(std::integral_constant<int, 3>{}, cnt); break;
-            default: batch(std::integral_constant<int, 4>{}, cnt); break;
+        uint32_t st = ring_lane + uint32_t(slot) * uint32_t(kStageBytes);
+#pragma unroll 1
+        for (int bi = 0; bi < kBPS && t < pe; ++bi, st += uint32_t(kSPS) * 128u) {
+          const int cnt = min(kSPS, pe - t);
+          const int k = u_end - t;  // steps left in the current unit (>= 1)
+          if (cnt == kSPS && k > kSPS) {
+            batch(std::integral_constant<int, 0>{}, cnt, st);
+          } else if (cnt == kSPS && !(u + 1 < nun && int(s_tab[u + 2] & kStepMask) - t <= kSPS)) {
+            switch (k) {
+              case 1: batch(std::integral_constant<int, 1>{}, cnt, st); break;
+              case 2: batch(std::integral_constant<int, 2>{}, cnt, st); break;
+              case 3: batch(std::integral_constant<int, 3>{}, cnt, st); break;
+              default: batch(std::integral_constant<int, 4>{}, cnt, st); break;
+            }
+          } else {
+            batch(std::integral_constant<int, -1>{}, cnt, st);
           }
-        } else {
-          batch(std::integral_constant<int, -1>{}, cnt);
         }
         __syncwarp();  // every lane has read its words of the stage: refill it
         if (qi + stages < nstage) issue(qi + stages, slot);
@@ -844,7 +849,7 @@ int gemv_lists_launch(int n, const vptq_linear_desc* const* descs, const void* x
   };
   size_t need = 0;
   bool placed = false;
-  for (int stages = 4; stages >= 2; --stages) {
+  for (int stages = 3; stages >= 2; --stages) {
     need = carve(stages);
     if (need <= limit) {
       placed = true;
