@@ -16,7 +16,8 @@ Printed JSON (one line, rank 0): the driver contract + `roofline`, `cpu_baseline
   value     tokens/s, inputs resident in HBM, one CUDA graph of the 224 launches per step
   e2e       tokens/s through the C ABI with HOST buffers: pinned x -> H2D -> 224 GEMVs -> D2H -> sync
   roofline  HBM: algorithmic bytes (packed indices + x + y of every launch) / step time
-  N > 1     tensor-parallel over out_features (one NCCL all-reduce per linear), strong scaling
+  N > 1     tensor-parallel over out_features; exchange fused into the GEMV over NVLink peer memory (tagged words;
+            --tp-mode nccl: one NCCL all-reduce per launch, the north_star form), strong scaling; `tp_check`
 """
 from __future__ import annotations
 
@@ -641,6 +642,11 @@ def run_ours(args):
                 line["module_api"] = module_level(m, stack, device, dtype, x_host, args.steps, args.warmup)
             except Exception as e:  # noqa: BLE001
                 line["module_api"] = {"error": repr(e)[:300]}
+        if world == 1 and not args.no_prefill:
+            try:
+                line["prefill"] = prefill_timing(m, q, stack, device, dtype)
+            except Exception as e:  # noqa: BLE001
+                line["prefill"] = {"error": repr(e)[:300]}
         if world == 1 and not args.no_ref_cuda:
             try:
                 line["ref_cuda"] = ref_cuda_timing(m, q, device, dtype)
@@ -734,6 +740,49 @@ def run_reference(args):
 # sm_100a by oracle/build_ref.sh) timed on the same box, eager, one launch pair per linear as the reference runs
 # them (csrc/quant_gemv.cu:241-294 + its sum(-1) epilogue; prefill: csrc/dequant.cu:227-287 + F.linear).
 # ------------------------------------------------------------------------------------------------
+def prefill_timing(m, q, stack, device, dtype, tokens=8192):
+    """BASELINE.json configs[2] (prefill, batch 4 x seq 2048 = 8192 tokens) on the three distinct linear shapes of one
+    decoder layer: vptq_b200_quant_gemm (prep + dequant into the workspace + hand-written tcgen05 GEMM) next to OUR
+    dequant kernel + cuBLAS through torch, and the tensor-pipe share of the bf16 sustained peak."""
+    import torch
+    from vptq_b200 import native
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1436.0))
+    out = {"tokens": tokens, "shapes": {}}
+    for name in ("q", "gate", "down"):
+        t = stack[0][name]
+        i, o, d = t["in"], t["out"], t["desc"]
+        x = torch.randn(tokens, i, device=device).to(dtype)
+        y = torch.empty(tokens, o, device=device, dtype=dtype)
+        W = torch.empty(o, i, device=device, dtype=dtype)
+
+        def med(fn, n=7):
+            fn(); torch.cuda.synchronize()
+            ts = []
+            for _ in range(n):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return sorted(ts)[len(ts) // 2]
+        ours = med(lambda: native.quant_gemm(d, x, y))
+
+        def deq_cublas():
+            native.dequant(d, W)
+            torch.nn.functional.linear(x, W)
+        cub = med(deq_cublas)
+        tf = 2.0 * tokens * i * o / (ours * 1e-3) / 1e12
+        out["shapes"][f"{name}_{o}x{i}"] = {"ms": round(ours, 4), "tflops": round(tf, 1), "frac_of_bf16_sustained": round(tf / peak, 3),
+                                            "our_dequant_plus_cublas_ms": round(cub, 4)}
+        del x, y, W
+    out["how"] = ("median of 7, CUDA events, whole op (x' prep + dequant + GEMM); flops = 2*T*I*O; peak = "
+                  "MEASURED_PEAKS.json bf16_tflops_sustained")
+    return out
+
+
 def ref_cuda_timing(m, q, device, dtype, prefill_tokens=8192):
     import importlib.util
     import torch
@@ -806,6 +855,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-pdl", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the BASELINE configs[2] prefill timings")
     ap.add_argument("--no-module-level", action="store_true", help="skip the VQuantLinear.forward / fuse(model) timings")
     ap.add_argument("--no-ref-cuda", action="store_true", help="skip timing the reference's own CUDA kernels (oracle/_ref)")
     ap.add_argument("--cpu-budget", type=float, default=15.0)
