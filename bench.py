@@ -599,7 +599,7 @@ def run_ours(args):
         sliced_on = lists_on
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "gemv_traffic.json")))
-            traffic = (tj["sliced"] if sliced_on else tj)["dram_bytes_per_token"] // (n_launch * world)
+            traffic = (tj["lists"] if sliced_on else tj)["dram_bytes_per_token"] // (n_launch * world)
         except Exception:
             pass
         line = {
@@ -622,6 +622,8 @@ def run_ours(args):
                     "wall_ms_per_step": round(wall_e2e / e2e_steps, 4)},
             "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                          "frac": round(achieved / peak, 4), "traffic": traffic,
+                         "traffic_source": "ncu dram__bytes_read+write per launch, profiles/gemv_traffic.json (one --set full "
+                                           "capture per shape, profiles/r02_ncu_shapes_metrics.csv); not measured in this run",
                          "kernel": ("gemv_lists_kernel<half,true> (csrc/gemv_lists.cu: 64 KiB codebook slices in shared "
                                     "memory, slice x tile index lists)") if sliced_on else
                                    "gemv_body<half,8,1,false,true> (entry points gemv_kernel / gemv_multi_kernel)",
@@ -630,6 +632,16 @@ def run_ours(args):
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 (of fallback)"},
             "clocks": clk,
         }
+        # resident bytes of this rank's weights: checkpoint tensors + load-time index lists of the decode kernel
+        mem = {"packed_index_bytes": 0, "list_bytes": 0, "codebook_bytes": 0}
+        for layer in stack:
+            for t in layer.values():
+                mem["packed_index_bytes"] += t["indices"].numel() * 4
+                mem["codebook_bytes"] += t["centroids"].numel() * 2 + (t["res_centroids"].numel() * 2 if t["res_centroids"] is not None else 0)
+                mem["list_bytes"] += sum(k.numel() * k.element_size() for k in getattr(t["desc"], "_keep", ())
+                                         if k.dtype == torch.int32)
+        mem["lists_over_packed"] = round(mem["list_bytes"] / max(mem["packed_index_bytes"], 1), 3)
+        line["resident_bytes"] = mem
         if world > 1:
             line["tp_check"] = check
             line["config"]["tp_mode"] = tp_mode
@@ -823,7 +835,7 @@ def ref_cuda_timing(m, q, device, dtype, prefill_tokens=8192):
         for n in names:
             out["us_per_shape"][n] = round(us, 2)
             per_layer_us += us
-        if prefill_tokens and (i, o) == (m["hidden"], m["hidden"]):
+        if prefill_tokens and names[0] in ("q", "gate", "down"):
             # the reference's prefill path on this shape: dequant kernel + cuBLAS (vptq/ops/quant_gemm.py:231-275)
             inv = torch.argsort(t["perm"].view(torch.uint16).to(torch.int64)).to(torch.uint16).view(torch.int16)
             dargs = (t["indices"], t["centroids"].view(1, -1, v), None,
@@ -839,7 +851,8 @@ def ref_cuda_timing(m, q, device, dtype, prefill_tokens=8192):
                 e0.record(); W = ref.dequant(*dargs); yy = torch.nn.functional.linear(xp, W); e1.record()
                 torch.cuda.synchronize()
                 tp_.append(e0.elapsed_time(e1))
-            prefill = {"shape": f"{o}x{i}", "tokens": prefill_tokens, "ms": round(sorted(tp_)[len(tp_) // 2], 4)}
+            prefill[f"{names[0]}_{o}x{i}"] = {"tokens": prefill_tokens, "ms": round(sorted(tp_)[len(tp_) // 2], 4)}
+            del xp, W
         del t
     out["tokens_per_s"] = round(1e6 / (per_layer_us * m["layers"]), 2)
     if prefill:
