@@ -230,6 +230,11 @@ VPTQ_B200_API int vptq_b200_quant_gemv_multi_ws(int32_t n, const vptq_linear_des
  *                   one, also written), and a launch with wait_slot >= 0 takes `x` = its local tagged buffer
  *                   (in_features / 2 words).  ys[l] still receives the plain local slice.  Only for launches
  *                   whose layers all carry index lists (list kernel), one token, out_features % 8 == 0.
+ *                   Buffer reuse is safe without any handshake as long as every launch of the chain waits for
+ *                   the launch that produced its x (wait_slot) and a buffer written by slot n is read only by
+ *                   slot n + 1: a rank that is about to overwrite the buffer (at slot n + k, k >= 2, of the same
+ *                   or the next token) has waited for the outputs of slot n + k - 1 >= n + 1 of EVERY rank, and
+ *                   a rank produces those only after its own launch n + 1 -- the reader -- has completed.
  */
 #define VPTQ_TP_PLAIN 0
 #define VPTQ_TP_TAGGED 1
