@@ -11,7 +11,7 @@ oracle/ref_shim.py, the reference's
   * dequant in the native 16-bit dtype (what the fallback would return to F.linear) -> W_ref16
 
 and stores inputs + outputs.  The committed fixtures are what pins oracle/vptq_oracle.py and
-oracle/vptq_oracle.py (tests/test_oracle_golden.py), and what the GPU parity tests compare the
+oracle/torch_port.py (tests/test_oracle_golden.py), and what the GPU parity tests compare the
 CUDA path against (tests/test_gpu_parity.py).
 
     python oracle/make_golden.py            # rewrites tests/golden/
