@@ -685,6 +685,9 @@ def _cpu_threads():
     look 60x slower than the box really is -- undo it (rank 0 is the only rank that runs the CPU arm)."""
     import torch
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # one thread per physical core: with all 128 hyper-threads of the GPU box the gather / GEMV mix of this path ran
+    # 4x SLOWER than with 64 (measured, round 2), so that would understate the CPU
+    n = n // 2 if n > 16 else n
     try:
         torch.set_num_threads(max(1, n))
     except Exception:
