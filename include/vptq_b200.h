@@ -94,7 +94,8 @@ typedef struct vptq_linear_desc {
   /* packed indices, int32 words [G][Ro][Wd], Ro = ceil(O/v), Wd = ceil(gs*(ib+rb)/32);
      field j of a row = bits [j*b, (j+1)*b) of its little-endian bit stream,
      field = idx | ridx << ib   (vptq/utils/pack.py:41-67).  Strides in 32-bit words. */
-  const int32_t* indices;
+  const int32_t* indices; /* may be NULL when lists_stream / lists_tab are given (decode-only descriptor: the packed
+                             words were dropped after the lists were built; only single-token GEMV calls work) */
   int64_t index_stride_codebook;
   int64_t index_stride_row;
 

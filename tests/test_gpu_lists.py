@@ -171,3 +171,27 @@ def test_lists_full_llama_shapes_match_generic(shape):
     yl, yg = _run(_desc(L, True), x).float(), _run(_desc(L, False), x).float()
     assert torch.isfinite(yl).all()
     assert float((yl - yg).abs().max()) <= 2.0 ** -9 * float(yg.abs().max())
+
+
+def test_decode_only_module_drops_the_packed_words():
+    """VQuantLinear.prepare(drop_packed=True): the lists replace the packed words (one copy of the indices); one-token
+    calls are unchanged, multi-token calls and dequant refuse loudly, reloading the checkpoint restores everything."""
+    from _gpu import from_t, make_module, x_to_t
+    L = vo.make_layer(in_features=2048, out_features=1024, vector_len=8, num_centroids=65536, num_res_centroids=256, seed=77)
+    m = make_module(L)
+    x_np = vo.make_x(3, 2048, "fp16", seed=1)
+    x = x_to_t(x_np, L)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    y1 = m(x[:1]).clone()
+    m.prepare(drop_packed=True)
+    assert m.indices.numel() == 0 and not m._desc_cache[0].indices
+    assert torch.equal(m(x[:1]), y1)
+    assert parity_error(from_t(y1), vo.quant_gemm(x_np[:1], L)) <= TOL["fp16"]
+    for bad in (x[:2], x):
+        with pytest.raises(RuntimeError, match="decode-only"):
+            m(bad)
+    with pytest.raises(RuntimeError):
+        m.dequant()
+    m.load_state_dict(sd)
+    assert parity_error(from_t(m(x)), vo.quant_gemm(x_np, L)) <= TOL["fp16"]
+    assert torch.equal(m(x[:1]), y1)

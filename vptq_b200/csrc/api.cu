@@ -104,8 +104,10 @@ int validate(const vptq_linear_desc* d, bool need_device) {
       return VPTQ_ERR_INVALID;
     }
   }
-  if (!d->indices || !d->centroids) {
-    set_error("indices / centroids must not be NULL");
+  // `indices` may be NULL for a decode-only descriptor that carries the index lists instead (the packed words were
+  // dropped after the lists were built): only single-token GEMV calls are possible then
+  if ((!d->indices && !(d->lists_stream && d->lists_tab)) || !d->centroids) {
+    set_error("indices (or the index lists) / centroids must not be NULL");
     return VPTQ_ERR_INVALID;
   }
   if (rb && !d->res_centroids) {
@@ -117,7 +119,7 @@ int validate(const vptq_linear_desc* d, bool need_device) {
     return VPTQ_ERR_INVALID;
   }
   const int64_t wd = (int64_t(d->group_size) * (ib + rb) + 31) / 32;
-  if (d->index_stride_row < wd) {
+  if (d->indices && d->index_stride_row < wd) {
     set_error("index_stride_row %lld < %lld packed words per row", (long long)d->index_stride_row, (long long)wd);
     return VPTQ_ERR_INVALID;
   }
@@ -144,6 +146,12 @@ int validate(const vptq_linear_desc* d, bool need_device) {
   return 0;
 }
 
+int need_packed(const vptq_linear_desc* d, const char* what) {
+  if (d->indices) return 0;
+  set_error("%s needs the packed index words, but this descriptor is decode-only (indices == NULL, index lists only)", what);
+  return VPTQ_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 }  // namespace vptq_b200
 
@@ -162,6 +170,7 @@ size_t vptq_b200_workspace_bytes(const vptq_linear_desc* desc, int32_t tokens, i
   if (tokens < 1) tokens = 1;
   switch (op) {
     case VPTQ_OP_GEMV: {
+      if (!desc->indices) return gemv_lists_workspace_bytes(*desc);
       // exact for the current device; without one (CPU-only host) the B200 geometry is assumed
       DeviceInfo b200;
       b200.sm_count = 148, b200.smem_optin = 232448, b200.cc_major = 10;
@@ -270,6 +279,7 @@ int vptq_b200_dequant(const vptq_linear_desc* desc, void* w_out, void* workspace
     set_error("dequant: w_out is NULL");
     return VPTQ_ERR_INVALID;
   }
+  if (int rc = need_packed(desc, "dequant")) return rc;
   return dequant_launch(*desc, w_out, workspace, workspace_bytes, static_cast<cudaStream_t>(stream));
 }
 
@@ -281,6 +291,7 @@ int vptq_b200_quant_gemm(const vptq_linear_desc* desc, const void* x, int64_t x_
     set_error("quant_gemm: bad x/y/tokens/strides");
     return VPTQ_ERR_INVALID;
   }
+  if (int rc = need_packed(desc, "quant_gemm")) return rc;
   return gemm_launch(*desc, x, x_stride, y, y_stride, tokens, workspace, workspace_bytes, flags,
                      static_cast<cudaStream_t>(stream));
 }
@@ -329,6 +340,8 @@ int vptq_b200_linear_host(const vptq_linear_desc* desc, const void* x_host, void
     set_error("linear_host: NULL buffer");
     return VPTQ_ERR_INVALID;
   }
+  if (tokens >= 3)
+    if (int rc = need_packed(desc, "linear_host (prefill)")) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t xb = size_t(tokens) * desc->in_features * 2, yb = size_t(tokens) * desc->out_features * 2;
   cudaError_t e = cudaMemcpyAsync(x_dev, x_host, xb, cudaMemcpyHostToDevice, s);

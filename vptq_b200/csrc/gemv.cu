@@ -358,6 +358,11 @@ int gemv_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
     const int rc = gemv_lists_launch(1, &dp, x, &yp, flags, stream, workspace, workspace_bytes);
     if (rc != VPTQ_ERR_UNSUPPORTED && rc != VPTQ_ERR_WORKSPACE) return rc;
   }
+  if (!d.indices) {
+    set_error("gemv: this descriptor is decode-only (indices == NULL): only single-token calls through the index "
+              "lists are possible (tokens %d, workspace %zu bytes)", tokens, workspace_bytes);
+    return VPTQ_ERR_UNSUPPORTED;
+  }
   GemvPlan pl;
   if (int rc = gemv_make_plan(d, tokens, *dev, &pl)) return rc;
   const size_t need = pl.ws_partials_bytes ? pl.ws_counters_bytes + pl.ws_partials_bytes : 0;
@@ -413,6 +418,11 @@ int gemv_multi_launch(int n, const vptq_linear_desc* const* descs, const void* x
               "lists, several tokens or no workspace: use VPTQ_TP_PLAIN)");
     return VPTQ_ERR_UNSUPPORTED;
   }
+  for (int l = 0; l < n; ++l)
+    if (!descs[l]->indices) {
+      set_error("gemv_multi: layer %d is decode-only (indices == NULL) and this launch cannot use the index lists", l);
+      return VPTQ_ERR_UNSUPPORTED;
+    }
   const vptq_linear_desc& d0 = *descs[0];
   double vol[kMaxFused], total = 0;
   for (int l = 0; l < n; ++l) {

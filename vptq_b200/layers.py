@@ -161,13 +161,29 @@ class VQuantLinear(nn.Module):
         # data_ptr catches .to() / re-assignment, _version catches in-place updates (load_state_dict, copy_)
         return tuple((a.data_ptr(), a.dtype, a._version) if a is not None else None for a in t) + (dtype, device)
 
-    def prepare(self, dtype: Optional[torch.dtype] = None) -> "VQuantLinear":
+    def prepare(self, dtype: Optional[torch.dtype] = None, drop_packed: bool = False) -> "VQuantLinear":
         """Build the C-ABI descriptor and its load-time derivatives (scale/bias in quantised order, the
         slice x tile index lists of the decode kernel) now instead of inside the first forward: call once
-        after loading the checkpoint, before capturing CUDA graphs."""
+        after loading the checkpoint, before capturing CUDA graphs.
+
+        drop_packed=True makes the module DECODE-ONLY: once the index lists exist the packed `indices` are freed
+        (4.2 instead of 7.2 bytes per index resident).  Calls with more than one token, `dequant()` and saving the
+        state_dict are no longer possible; reloading a checkpoint restores them."""
         dtype = dtype or self.centroids.weight.dtype
         x = torch.zeros(1, self.in_features, dtype=dtype, device=self.centroids.weight.device)
-        self.forward(x)
+        if drop_packed:
+            if not self.is_indice_packed:
+                raise RuntimeError("drop_packed needs a packed checkpoint (is_indice_packed=True)")
+            self._desc_cache, self._desc_key = [], None
+            self._drop_request = True
+        try:
+            self.forward(x)
+        finally:
+            self._drop_request = False
+        if drop_packed:
+            with torch.no_grad():
+                self.indices.data = torch.empty(0, dtype=self.indices.dtype, device=self.indices.device)
+            self._packed, self._drop_packed = None, True
         return self
 
     def __getstate__(self):
@@ -190,6 +206,11 @@ class VQuantLinear(nn.Module):
             return self.proxy_error_forward(W, H)   # quantizer-side debugging aid
         t = self._tensors()
         key = self._cache_key(t, x.dtype, x.device)
+        if getattr(self, "_drop_packed", False):
+            if self.indices.numel() == 0 and self._desc_cache:
+                key = self._desc_key                  # decode-only: the descriptor no longer depends on `indices`
+            else:
+                self._drop_packed = False             # a checkpoint was loaded again: a full module once more
         if key != self._desc_key:                    # parameters were moved / reloaded / updated in place
             self._desc_cache = []
             self._desc_key = key
@@ -203,10 +224,14 @@ class VQuantLinear(nn.Module):
             num_res_centroids=self.num_res_centroids, is_indice_packed=True, group_size=self.group_size,
             outlier_size=self.outlier_size, in_features=self.in_features, out_features=self.out_features,
             padding=self.padding, outlier_padding=self.outlier_padding,
-            vector_quant_dim=self.vector_quant_dim, _desc_cache=self._desc_cache)
+            vector_quant_dim=self.vector_quant_dim, _desc_cache=self._desc_cache,
+            _drop_packed=getattr(self, "_drop_request", False))
 
     def dequant(self) -> torch.Tensor:
         """Dense [out_features, in_features] weight through the CUDA dequant kernel."""
+        if getattr(self, "_drop_packed", False) and self.indices.numel() == 0:
+            raise RuntimeError("this VQuantLinear is decode-only (prepare(drop_packed=True)): the packed index words "
+                               "dequant needs were freed; reload the checkpoint to get them back")
         indices, cent, resc, outi, outc, perm, ws, wb, _ = self._tensors()
         return ops.dequant(
             indices=self._packed_indices(), centroids=cent, outlier_indices=outi, outlier_centroids=outc,

@@ -160,7 +160,7 @@ def make_desc(*, dtype: torch.dtype, in_features: int, out_features: int, vector
               outlier_indices: Optional[torch.Tensor], outlier_centroids: Optional[torch.Tensor],
               perm: Optional[torch.Tensor], weight_scale: Optional[torch.Tensor],
               weight_bias: Optional[torch.Tensor], bias: Optional[torch.Tensor],
-              derive: bool = True, lists: Optional[bool] = None) -> LinearDesc:
+              derive: bool = True, lists: Optional[bool] = None, drop_packed: bool = False) -> LinearDesc:
     """Describe one layer's tensors for the C ABI.  Tensors are borrowed: keep them alive.
 
     With `derive` (default) the load-time derivatives the ABI accepts are built here, once:
@@ -171,6 +171,10 @@ def make_desc(*, dtype: torch.dtype, in_features: int, out_features: int, vector
     large-codebook layers gather from shared memory; costs 4 bytes per index (+ ~6 % padding) on top
     of the packed words (3 bytes per index for the 65536+256 configuration).  None = the
     VPTQ_B200_LISTS environment variable (default on); ignored for layers the list kernel does not cover.
+
+    `drop_packed`: decode-only descriptor -- once the lists are built the descriptor forgets the packed words
+    (`indices` = NULL), so the caller may free them: 4.2 instead of 7.2 bytes per index.  Multi-token calls,
+    dequant and prefill then return VPTQ_ERR_UNSUPPORTED.  Refused for layers without lists.
     """
     if indices.dtype != torch.int32:
         raise RuntimeError("`indices` must be packed int32 words (is_indice_packed=True); "
@@ -220,6 +224,10 @@ def make_desc(*, dtype: torch.dtype, in_features: int, out_features: int, vector
                                               out_features=d.out_features, perm=perm)
         d.lists_stream, d.lists_tab, d.lists_tile_cols = stream.data_ptr(), tab.data_ptr(), int(tcw)
         d._keep = d._keep + (stream, tab)
+    if drop_packed:
+        if not d.lists_stream:
+            raise RuntimeError("drop_packed: this layer has no index lists (not eligible, or lists=False)")
+        d.indices = None
     return d
 
 

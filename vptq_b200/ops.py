@@ -24,7 +24,7 @@ __all__ = ["dequant", "quant_gemm", "quant_gemv_v2"]
 def _desc(*, dtype, indices, centroids, outlier_indices, outlier_centroids, residual_centroids, perm,
           weight_scale, weight_bias, bias, vector_len, outlier_vector_len, num_codebooks, num_centroids,
           num_outlier_centroids, num_res_centroids, group_size, outlier_size, in_features, out_features,
-          derive=True, lists=None):
+          derive=True, lists=None, drop_packed=False):
     if perm is not None and perm.dtype not in (torch.int16, torch.uint16):
         # unpacked checkpoints keep perm as int64 (vqlinear.py:191-196)
         perm = perm.to(torch.int64).to(torch.uint16).contiguous()
@@ -35,7 +35,7 @@ def _desc(*, dtype, indices, centroids, outlier_indices, outlier_centroids, resi
         outlier_vector_len=outlier_vector_len, num_outlier_centroids=num_outlier_centroids, indices=indices,
         centroids=centroids, res_centroids=residual_centroids, outlier_indices=outlier_indices,
         outlier_centroids=outlier_centroids, perm=perm, weight_scale=weight_scale, weight_bias=weight_bias,
-        bias=bias, derive=derive, lists=lists), perm
+        bias=bias, derive=derive, lists=lists, drop_packed=drop_packed), perm
 
 
 def dequant(
@@ -117,6 +117,7 @@ def quant_gemm(
     outlier_padding: int,
     vector_quant_dim: str = "out",
     _desc_cache: Optional[list] = None,
+    _drop_packed: bool = False,
 ) -> torch.Tensor:
     """y = x @ W^T + bias for one VPTQ layer (reference: vptq/ops/quant_gemm.py:161-275)."""
     if vector_quant_dim == "in":
@@ -142,7 +143,7 @@ def quant_gemm(
             group_size=group_size, outlier_size=outlier_size, in_features=in_features, out_features=out_features,
             # a one-off descriptor (reference-style direct call) must not pay for re-bucketing the whole layer:
             # the slice x tile lists are built only when the caller keeps the descriptor (VQuantLinear does)
-            lists=None if _desc_cache is not None else False)
+            lists=None if _desc_cache is not None else False, drop_packed=_drop_packed)
         if _desc_cache is not None:
             _desc_cache.extend([desc, perm_])   # keep the converted perm alive with the descriptor
     x2d = x.reshape(-1, in_features)
