@@ -243,7 +243,11 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   uint64_t* full = &bars[2 + warp * stages];
 
   auto stamp = [&](int slot) {
+#ifdef VPTQ_B200_PROF_WARPS
+    if (mp.prof && tid == 0 && blockIdx.x == 0) {
+#else
     if (mp.prof && tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1)) {
+#endif
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       mp.prof[(blockIdx.x == 0 ? 0 : 16) + slot] = t;
@@ -548,6 +552,13 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
     if (u < nun && int(s_tab[u] & kStepMask) < t_end) flush(false);
   }
   stamp(6);  // warp 0 finished its run
+#ifdef VPTQ_B200_PROF_WARPS  // developer build: when did every warp of the first CTA finish its run?
+  if (mp.prof && lane == 0 && blockIdx.x == 0) {
+    unsigned long long tw;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw));
+    mp.prof[16 + warp] = tw;
+  }
+#endif
   __syncthreads();
   stamp(7);
 
