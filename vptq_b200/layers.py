@@ -186,6 +186,14 @@ class VQuantLinear(nn.Module):
             self._packed, self._drop_packed = None, True
         return self
 
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        # a decode-only module (prepare(drop_packed=True)) freed its packed words: make room for the checkpoint's
+        src = state_dict.get(prefix + "indices")
+        if src is not None and self.indices.numel() == 0 and src.numel() > 0:
+            with torch.no_grad():
+                self.indices.data = torch.empty(src.shape, dtype=self.indices.dtype, device=self.indices.device)
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
     def __getstate__(self):
         # the cached descriptor holds raw pointers (ctypes): never pickled or deep-copied
         st = self.__dict__.copy()
