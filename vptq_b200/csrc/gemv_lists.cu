@@ -46,8 +46,16 @@ namespace {
 constexpr int kSliceEntries = 4096;
 constexpr int kSliceBytes = kSliceEntries * 16;  // 64 KiB
 constexpr int kTileMax = 4096;
-constexpr int kLW = 16, kLT = kLW * 32;  // warps, threads per CTA
-constexpr int kSPS = 4;                  // steps (32 entries, 128 bytes each) per batch: loads of 4 steps in flight
+#ifndef VPTQ_LISTS_WARPS
+#define VPTQ_LISTS_WARPS 16
+#endif
+#ifndef VPTQ_LISTS_BATCH
+#define VPTQ_LISTS_BATCH 4
+#endif
+constexpr int kLW = VPTQ_LISTS_WARPS, kLT = kLW * 32;  // warps, threads per CTA
+constexpr int kSPS = VPTQ_LISTS_BATCH;   // steps (32 entries, 128 bytes each) per batch: loads of kSPS steps in flight
+static_assert(kSPS >= 2 && kSPS <= 4 && kLW <= 32, "batch variants are written out for 2..4 steps");
+constexpr int kEnd3 = kSPS >= 3 ? 3 : 2;  // (switch label 3 is unreachable for 2-step batches)
 constexpr int kBPS = 2;                  // batches per ring stage (one TMA copy / one barrier wait per 8 steps)
 constexpr int kStSteps = kSPS * kBPS;
 constexpr int kStageBytes = kStSteps * 128;
@@ -280,10 +288,11 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   // residual codebook (<= 256 entries of 16 bytes), stored 8 times: copy k of entry i sits at 16-byte slot
   // i*8 + k and lane L reads copy L mod 8, so the 8 lanes of a quarter-warp always hit 8 different bank groups.
   // Thread t fills slots t, t + 512, ...: consecutive lanes write consecutive slots (conflict-free stores).
-  uint4 res_entry[(256 * kResRep) / kLT];
+  constexpr int kResFill = (256 * kResRep + kLT - 1) / kLT;
+  uint4 res_entry[kResFill];
   if constexpr (RES) {
 #pragma unroll
-    for (int j = 0; j < (256 * kResRep) / kLT; ++j) {
+    for (int j = 0; j < kResFill; ++j) {
       const int slot = tid + j * kLT;
       res_entry[j] = make_uint4(0u, 0u, 0u, 0u);
       if (slot < L.Kr * kResRep)
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
 
   if constexpr (RES) {
 #pragma unroll
-    for (int j = 0; j < (256 * kResRep) / kLT; ++j) {
+    for (int j = 0; j < kResFill; ++j) {
       const int slot = tid + j * kLT;
       if (slot < L.Kr * kResRep) sts_v4(smem_u32(s_res) + uint32_t(slot) * 16u, res_entry[j]);
     }
@@ -536,8 +545,8 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
             switch (k) {
               case 1: batch(std::integral_constant<int, 1>{}, cnt, st); break;
               case 2: batch(std::integral_constant<int, 2>{}, cnt, st); break;
-              case 3: batch(std::integral_constant<int, 3>{}, cnt, st); break;
-              default: batch(std::integral_constant<int, 4>{}, cnt, st); break;
+              case 3: batch(std::integral_constant<int, kEnd3>{}, cnt, st); break;
+              default: batch(std::integral_constant<int, kSPS>{}, cnt, st); break;
             }
           } else {
             batch(std::integral_constant<int, -1>{}, cnt, st);

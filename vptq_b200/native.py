@@ -17,7 +17,7 @@ import torch
 from . import lists as _lists
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvptq_b200.so")
+LIB_PATH = os.environ.get("VPTQ_B200_LIB") or os.path.join(_HERE, "libvptq_b200.so")   # (env: developer builds)
 
 VPTQ_FP16, VPTQ_BF16 = 0, 1
 OP_GEMV, OP_DEQUANT, OP_GEMM, OP_GEMV_V2 = 0, 1, 2, 3
