@@ -596,10 +596,10 @@ def run_ours(args):
         abytes = algorithmic_bytes(m, q, 1, world)         # per rank and step
         achieved = abytes / (ms_step * 1e-3) / 1e9
         traffic = None
-        sliced_on = lists_on
+        uses_lists = lists_on
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "gemv_traffic.json")))
-            traffic = (tj["lists"] if sliced_on else tj)["dram_bytes_per_token"] // (n_launch * world)
+            traffic = (tj["lists"] if uses_lists else tj)["dram_bytes_per_token"] // (n_launch * world)
         except Exception:
             pass
         line = {
@@ -625,7 +625,7 @@ def run_ours(args):
                          "traffic_source": "ncu dram__bytes_read+write per launch, profiles/gemv_traffic.json (one --set full "
                                            "capture per shape, profiles/r02_ncu_shapes_metrics.csv); not measured in this run",
                          "kernel": ("gemv_lists_kernel<half,true> (csrc/gemv_lists.cu: 64 KiB codebook slices in shared "
-                                    "memory, slice x tile index lists)") if sliced_on else
+                                    "memory, slice x tile index lists)") if uses_lists else
                                    "gemv_body<half,8,1,false,true> (entry points gemv_kernel / gemv_multi_kernel)",
                          "algorithmic_bytes_per_launch": abytes // n_launch,
                          "avg_launch_us": round(ms_step * 1e3 / n_launch, 3),
