@@ -95,3 +95,19 @@ def test_prefill_large_tokens_property():
     idx = torch.randint(0, 8192, (64,), generator=torch.Generator().manual_seed(1)).tolist()
     ref = torch.cat([m(x1[i:i + 1]) for i in idx]).float()
     assert (ref - y1[idx]).abs().max() <= 1e-3 * scale
+
+
+def test_prep_path_still_matches(monkeypatch):
+    """VPTQ_B200_GEMM_PREP=1 forces the round-1 route (x' prep pass + quantised-order Wq) for a shape that takes the
+    prep-free route by default: both must match the oracle."""
+    from _gpu import from_t, make_module, x_to_t
+    L = vo.make_layer(in_features=1024, out_features=512, vector_len=8, num_centroids=65536, num_res_centroids=256, seed=17)
+    m = make_module(L)
+    x_np = vo.make_x(200, 1024, "fp16", seed=3)
+    x = x_to_t(x_np, L)
+    y_star = vo.quant_gemm(x_np, L)
+    y_direct = from_t(m(x))
+    monkeypatch.setenv("VPTQ_B200_GEMM_PREP", "1")
+    y_prep = from_t(m(x))
+    for y in (y_direct, y_prep):
+        assert parity_error(y, y_star) <= TOL["fp16"]

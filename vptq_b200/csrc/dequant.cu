@@ -228,6 +228,123 @@ __global__ void __launch_bounds__(DQ_THREADS) dequant_q8_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fast path of the ORIGINAL-order dequant (the reference op, and the B operand of the prep-free prefill
+// path), vector_len 8, one codebook group, no outlier columns: one CTA per index row.  The row's packed
+// words are staged in shared memory once (TMA), the residual table is bank-replicated there; a thread
+// owns 8 CONSECUTIVE ORIGINAL columns f..f+7: it looks up their quantised columns (inverse permutation,
+// one 16-byte load), extracts the 8 fields from the staged row (any bit offset), gathers the 8 codebook
+// entries (8 independent 16-byte loads in flight; the generic kernel has two), applies
+// (C + R) * scale[f] + wbias[f] in fp32, rounds once, transposes the 8x8 block in registers and writes one
+// 16-byte vector per output row: every warp store covers 512 contiguous bytes.
+// ---------------------------------------------------------------------------------------------
+constexpr int DO_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(DO_THREADS) dequant_o8_kernel(const __grid_constant__ DequantParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int b = p.ib + p.rb;
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nw = (p.I * b + 31) >> 5;                    // packed words of one row
+  const uint32_t row_bytes = (uint32_t(nw) * 4u + 8u + 127u) & ~127u;  // (+ one readable pad word)
+  uint32_t* s_idx = reinterpret_cast<uint32_t*>(smem);
+  uint8_t* s_res = smem + row_bytes;
+  __shared__ uint64_t bar;
+  const uint32_t* row = p.indices + int64_t(r) * p.idx_stride_r;
+  const bool tma_ok = ((reinterpret_cast<uintptr_t>(row) & 15u) == 0) && ((nw & 3) == 0);
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+    s_idx[nw] = 0u, s_idx[nw + 1] = 0u;
+  }
+  __syncthreads();
+  if (tma_ok) {
+    if (tid == 0) {
+      mbar_arrive_expect_tx(&bar, uint32_t(nw) * 4u);
+      for (uint32_t off = 0; off < uint32_t(nw) * 4u; off += 32768u)
+        tma_bulk_g2s(reinterpret_cast<uint8_t*>(s_idx) + off, reinterpret_cast<const uint8_t*>(row) + off,
+                     min(32768u, uint32_t(nw) * 4u - off), &bar, policy_evict_first());
+    }
+  } else {
+    for (int w = tid; w < nw; w += DO_THREADS) s_idx[w] = ldg_nc_u32(row + w);
+  }
+  const T* rcb = reinterpret_cast<const T*>(p.res_centroids);
+  const int Kr = p.rb ? (1 << p.rb) : 0;
+  for (int slot = tid; slot < Kr * 8; slot += DO_THREADS)   // copy k of entry i at slot i*8+k: conflict-free fill
+    sts_v4(smem_u32(s_res) + uint32_t(slot) * 16u,
+           ldg_nc_v4(reinterpret_cast<const uint8_t*>(rcb) + size_t(slot >> 3) * 16, policy_evict_last()));
+  __syncthreads();
+  if (tma_ok) mbar_wait(&bar, 0);
+
+  const uint32_t fmask = b >= 32 ? 0xffffffffu : ((1u << b) - 1u), imask = (1u << p.ib) - 1u;
+  const uint8_t* cb = reinterpret_cast<const uint8_t*>(p.centroids);
+  const uint32_t res_lane = smem_u32(s_res) + (lane & 7) * 16;
+  const uint64_t keep = policy_evict_last();
+  const T* scale = reinterpret_cast<const T*>(p.scale);
+  const T* wbias = reinterpret_cast<const T*>(p.wbias);
+  T* out = reinterpret_cast<T*>(p.out);
+
+  for (int f0 = tid * 8; f0 < p.I; f0 += DO_THREADS * 8) {   // (I % 8 == 0)
+    uint32_t col[8];
+    if (p.inv_perm) {
+      const uint4 q = *reinterpret_cast<const uint4*>(p.inv_perm + f0);
+      col[0] = q.x & 0xffffu, col[1] = q.x >> 16, col[2] = q.y & 0xffffu, col[3] = q.y >> 16;
+      col[4] = q.z & 0xffffu, col[5] = q.z >> 16, col[6] = q.w & 0xffffu, col[7] = q.w >> 16;
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) col[k] = uint32_t(f0 + k);
+    }
+    uint32_t fld[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t bit = col[k] * uint32_t(b), w = bit >> 5;
+      fld[k] = __funnelshift_r(s_idx[w], s_idx[w + 1], bit & 31u) & fmask;
+    }
+    uint4 cw[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cw[k] = ldg_nc_v4(cb + size_t(fld[k] & imask) * 16, keep);
+    uint4 scv = make_uint4(0u, 0u, 0u, 0u), wbv = scv;
+    if (scale) {
+      scv = *reinterpret_cast<const uint4*>(scale + f0);
+      wbv = *reinterpret_cast<const uint4*>(wbias + f0);
+    }
+    const uint32_t scw[4] = {scv.x, scv.y, scv.z, scv.w}, wbw[4] = {wbv.x, wbv.y, wbv.z, wbv.w};
+    uint32_t hv[8][4];  // column k, outputs (2i, 2i+1) packed -- after scale / bias, rounded once
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint4 rw = make_uint4(0u, 0u, 0u, 0u);
+      if (p.rb) rw = lds_v4(res_lane + (fld[k] >> p.ib) * 128);
+      const float2 s2 = DT<T>::unpack2(scw[k >> 1]), b2 = DT<T>::unpack2(wbw[k >> 1]);
+      const float sc = scale ? ((k & 1) ? s2.y : s2.x) : 1.f, wb = scale ? ((k & 1) ? b2.y : b2.x) : 0.f;
+      const uint32_t cwk[4] = {cw[k].x, cw[k].y, cw[k].z, cw[k].w}, rwk[4] = {rw.x, rw.y, rw.z, rw.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float2 c2 = DT<T>::unpack2(cwk[i]);
+        if (p.rb) {
+          const float2 r2 = DT<T>::unpack2(rwk[i]);
+          c2.x += r2.x, c2.y += r2.y;
+        }
+        hv[k][i] = DT<T>::pack2(fmaf(c2.x, sc, wb), fmaf(c2.y, sc, wb));
+      }
+    }
+    // 8x8 transpose: output row e takes element e of each of the 8 columns
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int o = r * 8 + e;
+      if (o < p.O) {
+        const uint32_t sel = (e & 1) ? 0x7632u : 0x5410u;
+        uint4 v;
+        v.x = __byte_perm(hv[0][e >> 1], hv[1][e >> 1], sel);
+        v.y = __byte_perm(hv[2][e >> 1], hv[3][e >> 1], sel);
+        v.z = __byte_perm(hv[4][e >> 1], hv[5][e >> 1], sel);
+        v.w = __byte_perm(hv[6][e >> 1], hv[7][e >> 1], sel);
+        *reinterpret_cast<uint4*>(out + int64_t(o) * p.ld + f0) = v;
+      }
+    }
+  }
+}
+
 // columns [I, ld) of every output row <- 0 (K padding of the GEMM operand)
 template <typename T>
 __global__ void dequant_zero_pad_kernel(T* out, int64_t ld, int I, int O) {
@@ -261,8 +378,22 @@ size_t dequant_workspace_bytes(const vptq_linear_desc& d) {
   return d.perm ? kZeroRegionBytes + align_up(size_t(d.in_features) * 2, 256) : 0;
 }
 
+// v = 8, one codebook group, no outlier columns, whole 8-column groups, 16-byte aligned rows, the packed row +
+// the replicated residual table fit in shared memory
+bool dequant_orig_fast_ok(const vptq_linear_desc& d, const void* w_out, int64_t ld) {
+  const bool outl = d.outlier_size > 0 && d.outlier_indices != nullptr;
+  if (d.vector_len != 8 || d.num_codebooks != 1 || outl || (d.in_features % 8) || (ld % 8)) return false;
+  if ((reinterpret_cast<uintptr_t>(w_out) & 15u) || (reinterpret_cast<uintptr_t>(d.weight_scale) & 15u) ||
+      (reinterpret_cast<uintptr_t>(d.weight_bias) & 15u))
+    return false;
+  const int b = ilog2(d.num_centroids) + (d.num_res_centroids > 0 ? ilog2(d.num_res_centroids) : 0);
+  const size_t row = (size_t(d.in_features) * b + 31) / 32 * 4 + 136;
+  const size_t res = d.num_res_centroids > 0 ? size_t(d.num_res_centroids) * 128 : 0;
+  return d.num_res_centroids <= 512 && row + res <= 190 * 1024;
+}
+
 int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size_t workspace_bytes,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, int64_t ld) {
   DequantParams p{};
   p.indices = reinterpret_cast<const uint32_t*>(d.indices);
   p.idx_stride_g = d.index_stride_codebook, p.idx_stride_r = d.index_stride_row;
@@ -278,7 +409,7 @@ int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size
   p.outlier_cb = p.S ? d.outlier_centroids : nullptr;
   p.scale = d.weight_scale, p.wbias = d.weight_bias;
   p.out = w_out;
-  p.ld = d.in_features;
+  p.ld = ld > 0 ? ld : d.in_features;
   p.quant_order = 0;
   p.inv_perm = nullptr;
   if (d.perm) {
@@ -287,9 +418,29 @@ int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size
       set_error("dequant: workspace %zu bytes < required %zu (inverse permutation)", workspace_bytes, need);
       return VPTQ_ERR_WORKSPACE;
     }
-    uint16_t* inv = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(workspace) + kZeroRegionBytes);
+    uint16_t* inv = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(workspace) + kZeroRegionBytes);  // (256-byte aligned)
     invert_perm_kernel<<<(d.in_features + 255) / 256, 256, 0, stream>>>(d.perm, inv, d.in_features);
     p.inv_perm = inv;
+  }
+  p.ld = ld > 0 ? ld : d.in_features;
+  if (dequant_orig_fast_ok(d, w_out, p.ld)) {
+    const int b = p.ib + p.rb;
+    const size_t nw = (size_t(d.in_features) * b + 31) / 32;
+    const size_t smem = ((nw * 4 + 8 + 127) & ~size_t(127)) + (p.rb ? (size_t(1) << p.rb) * 128 : 0);
+    dim3 grid(unsigned(p.Ro));
+    if (d.dtype == VPTQ_FP16) {
+      if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(dequant_o8_kernel<__half>), 200 * 1024)) return rc;
+      dequant_o8_kernel<__half><<<grid, DO_THREADS, smem, stream>>>(p);
+    } else {
+      if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(dequant_o8_kernel<__nv_bfloat16>), 200 * 1024)) return rc;
+      dequant_o8_kernel<__nv_bfloat16><<<grid, DO_THREADS, smem, stream>>>(p);
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("dequant (original order, fast path) launch: %s", cudaGetErrorString(e));
+      return VPTQ_ERR_CUDA;
+    }
+    return 0;
   }
   const int rc = d.dtype == VPTQ_FP16 ? launch_v<__half>(p, d.vector_len, stream)
                                       : launch_v<__nv_bfloat16>(p, d.vector_len, stream);

@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.cuh"
@@ -304,7 +305,7 @@ gemm_tn_tcgen05(const __grid_constant__ CUtensorMap map_a, const __grid_constant
       mbar_wait(&acc_full[a], (nt / ACC_STAGES) & 1);
       tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
-      const float rb = m < p.T ? p.rowbias[m] : 0.f;
+      const float rb = (p.rowbias && m < p.T) ? p.rowbias[m] : 0.f;
       T* yrow = reinterpret_cast<T*>(p.y) + int64_t(m) * p.y_stride;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -421,6 +422,40 @@ int gemm_launch(const vptq_linear_desc& d, const void* x, int64_t x_stride, void
   void* xq = ws + w.off_xq;
   void* wq = ws + w.off_wq;
   const int is_bf16 = d.dtype == VPTQ_BF16;
+
+  // Prep-free path: W in ORIGINAL column order with scale and weight_bias folded in (what the reference's dequant
+  // returns, csrc/kernels/dequant.cuh:9-115) through the 8-columns-per-thread dequant, and x handed to TMA as it
+  // is -- no x' pass over the tokens, no rowbias.  Needs whole BK blocks (in_features % 64 == 0) and TMA-able x rows.
+  const bool direct = std::getenv("VPTQ_B200_GEMM_PREP") == nullptr && int64_t(d.in_features) == w.kpad &&
+                      (reinterpret_cast<uintptr_t>(x) & 15u) == 0 && (x_stride % 8) == 0 &&
+                      dequant_orig_fast_ok(d, ws + kZeroRegionBytes + align_up(size_t(d.in_features) * 2, 1024), w.kpad);
+  if (direct) {
+    void* wo = ws + kZeroRegionBytes + align_up(size_t(d.in_features) * 2, 1024);  // behind the inverse permutation
+    if (int rc = dequant_launch(d, wo, workspace, workspace_bytes, stream, w.kpad)) return rc;
+    CUtensorMap map_a, map_b;
+    if (int rc = make_map(&map_a, is_bf16, x, tokens, w.kpad, x_stride, BM)) return rc;
+    if (int rc = make_map(&map_b, is_bf16, wo, d.out_features, w.kpad, w.kpad, BN)) return rc;
+    GemmParams p{};
+    p.bias = d.bias, p.rowbias = nullptr, p.y = y, p.y_stride = y_stride;
+    p.T = tokens, p.O = d.out_features, p.K = int(w.kpad), p.is_bf16 = is_bf16;
+    const DeviceInfo* dev = device_info();
+    if (!dev) return VPTQ_ERR_CUDA;
+    const int ntiles = ((d.out_features + BN - 1) / BN) * ((tokens + BM - 1) / BM);
+    dim3 grid(unsigned(std::min(ntiles, dev->sm_count)));
+    if (is_bf16) {
+      if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(gemm_tn_tcgen05<__nv_bfloat16>), GEMM_SMEM)) return rc;
+      gemm_tn_tcgen05<__nv_bfloat16><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(map_a, map_b, p);
+    } else {
+      if (int rc = ensure_smem_attr(reinterpret_cast<const void*>(gemm_tn_tcgen05<__half>), GEMM_SMEM)) return rc;
+      gemm_tn_tcgen05<__half><<<grid, GEMM_THREADS, GEMM_SMEM, stream>>>(map_a, map_b, p);
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      set_error("quant_gemm launch: %s", cudaGetErrorString(e));
+      return VPTQ_ERR_CUDA;
+    }
+    return 0;
+  }
 
   // 1. x' and rowbias
   const size_t prep_smem = align_up(size_t(d.in_features) * 2, 16);

@@ -108,8 +108,10 @@ int tp_untag_launch(const void* tagged, void* y, int n, const vptq_tp_exchange& 
 // dequant
 // -------------------------------------------------------------------------------------------
 size_t dequant_workspace_bytes(const vptq_linear_desc& d);
+// ld: elements between output rows (0 = in_features)
 int dequant_launch(const vptq_linear_desc& d, void* w_out, void* workspace, size_t workspace_bytes,
-                   cudaStream_t stream);
+                   cudaStream_t stream, int64_t ld = 0);
+bool dequant_orig_fast_ok(const vptq_linear_desc& d, const void* w_out, int64_t ld);  // 8-columns-per-thread path applies
 
 // -------------------------------------------------------------------------------------------
 // prefill GEMM (tcgen05)
