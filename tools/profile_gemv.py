@@ -27,7 +27,7 @@ prof = torch.zeros(32, dtype=torch.int64, device=dev)
 NAMES = ["start", "bar_init", "issued+staged", "phaseA", "cb_wait+replicate", "pdl_wait", "phaseB+sync", "cluster_wait",
          "main(warp0)", "leader_wait", "end"]
 if os.environ.get("VPTQ_B200_LISTS", native.LISTS_DEFAULT) != "0":   # stamps of csrc/gemv_lists.cu
-    NAMES = ["start", "loads+sync", "pdl_wait", "ring+res", "x'+sync", "slice_wait", "main(warp0)", "sync", "arrive",
+    NAMES = ["start", "loads+sync", "ring,res+pdl_wait", "x issued", "x'+sync", "slice_wait", "main(warp0)", "sync", "arrive",
              "end", "-"]
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 out = {}

@@ -32,7 +32,7 @@ with torch.cuda.stream(s):
         g.replay()
     s.synchronize()
 st = prof.cpu().view(nslots, 32).tolist()
-NAMES = ["start", "loads+sync", "pdl_wait", "ring+res", "x'+sync", "slice_wait", "main(w0)", "sync", "arrive", "end"]
+NAMES = ["start", "loads+sync", "ring,res+pdl_wait", "x issued", "x'+sync", "slice_wait", "main(w0)", "sync", "arrive", "end"]
 t0 = min(r[0] for r in st if r[0])
 order = sorted(range(nslots), key=lambda i: st[i][0])
 prev_end = None

@@ -347,8 +347,19 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
                    pol_stream);
     }
   };
-  // -------- x arrives from the previous kernel.  Its (coalesced) loads are issued first and complete while
-  // lane 0 of every warp queues the ring copies behind the slice copies in the TMA unit ---------------------
+  // -------- everything that does not depend on x is queued first: the ring copies of this warp's first stages and
+  // the replicated residual table -- a CTA usually starts a few microseconds before the previous kernel has
+  // finished, so this is hidden behind griddepcontrol.wait -----------------------------------------------------
+  for (int qi = 0; qi < min(stages, nstage); ++qi) issue(qi, qi);
+
+  if constexpr (RES) {
+#pragma unroll
+    for (int j = 0; j < kResFill; ++j) {
+      const int slot = tid + j * kLT;
+      if (slot < L.Kr * kResRep) sts_v4(smem_u32(s_res) + uint32_t(slot) * 16u, res_entry[j]);
+    }
+  }
+  // -------- x arrives from the previous kernel: one coalesced 128-bit load per thread ---------------------------
   pdl_wait_prior_grid();
   const bool tagged = mp.tp_world > 1 && mp.tp_format == VPTQ_TP_TAGGED;
   // tag of the words this launch writes / expects in its x: run number * launches per token + slot + 1
@@ -383,15 +394,6 @@ __global__ void __launch_bounds__(kLT, 1) gemv_lists_kernel(const __grid_constan
   } else {
     if (colA) xa = load8<T>(x, fA, fAend, 0);
     if (colB) xb = load8<T>(x, fB, fBend, 0);
-  }
-  for (int qi = 0; qi < min(stages, nstage); ++qi) issue(qi, qi);
-
-  if constexpr (RES) {
-#pragma unroll
-    for (int j = 0; j < kResFill; ++j) {
-      const int slot = tid + j * kLT;
-      if (slot < L.Kr * kResRep) sts_v4(smem_u32(s_res) + uint32_t(slot) * 16u, res_entry[j]);
-    }
   }
   stamp(3);
   // -------- x'[f] = x[f] * scale[f] -------------------------------------------------------------------------
