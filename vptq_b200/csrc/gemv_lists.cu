@@ -15,7 +15,9 @@
 //     copies), the 8x bank-replicated residual table and one or two x' tiles (x[f] * scale[f], a coalesced
 //     128-bit load per thread -- perm was folded into the entries at load time);
 //   * the CTA cuts its step range (32 entries per step) into 16 equal runs, one per warp, whatever the unit
-//     boundaries are.  A warp streams its run through a private TMA ring (4 steps = 512 B per stage); per
+//     boundaries are.  A warp streams its run through a private TMA ring (8 steps = 1 KiB per stage) and works in
+//     batches of 4 steps (12 gathers in flight per lane; where a unit ends inside a batch the flush sits at a
+//     compile-time position: five straight-line batch variants, no per-step test); per
 //     entry a lane does LDS.32 (entry), LDS.128 (main), LDS.128 (residual), LDS.U16 (x'), then c + r in
 //     packed 16-bit arithmetic (exactly the reference's ADD2, csrc/kernels/quant_gemv.cuh:124-127) and 8
 //     mixed-precision FMAs into fp32 accumulators (fma.rn.f32.f16 -> SASS FHFMA);
@@ -28,7 +30,12 @@
 //     measured at 4-8 us of tail per launch).  Row blocks of 32 index rows carry an arrival counter (units,
 //     not CTAs); the CTA whose arrival completes a block converts its rows back, adds bias, writes y and
 //     zeroes the accumulators and the counter again.  No second kernel (the reference launches `sum(-1)`,
-//     csrc/quant_gemv.cu:235), no spinning on other CTAs.
+//     csrc/quant_gemv.cu:235), no spinning on other CTAs;
+//   * tensor parallelism (vptq_tp_exchange): the thread that completes an index row also stores it into every
+//     peer's buffer over NVLink -- as tagged 8-byte words {2 values, tag} that the consumer launch re-reads
+//     until the tag is current (no fence, no flag, no NCCL call), or plain + epoch flags.
+// Measured variants that lost (more warps with smaller batches, entry prefetch, returning atomics, a scan of
+// the touched rows instead of counters) are listed in DESIGN.md section 3.
 // Mathematics and reference citations: gemv_kernel.cuh (the reference's kernel is
 // csrc/kernels/quant_gemv.cuh:11-186; nothing of its structure is used here).
 #include <algorithm>
