@@ -253,11 +253,37 @@ def _stream(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _on_device:
+    """`with torch.cuda.device(dev)` only when dev is not already current (the context manager costs microseconds on
+    a path whose kernel takes ten)."""
+
+    def __init__(self, dev: torch.device):
+        idx = dev.index if dev.index is not None else torch.cuda.current_device()
+        self.ctx = None if idx == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+def _ws_bytes_cached(desc: LinearDesc, tokens: int, op: int) -> int:
+    cache = desc.__dict__.setdefault("_ws_cache", {})
+    key = (min(tokens, 4) if op == OP_GEMV else tokens, op)     # the GEMV plans passes of at most 4 tokens
+    v = cache.get(key)
+    if v is None:
+        v = cache[key] = workspace_bytes(desc, tokens, op)
+    return v
+
+
 def quant_gemv(desc: LinearDesc, x2d: torch.Tensor, y2d: torch.Tensor, flags: int = 0) -> None:
     dev = x2d.device
     tokens = x2d.shape[0]
-    with torch.cuda.device(dev):
-        ws = workspace(dev, workspace_bytes(desc, tokens, OP_GEMV))
+    with _on_device(dev):
+        ws = workspace(dev, _ws_bytes_cached(desc, tokens, OP_GEMV))
         rc = lib().vptq_b200_quant_gemv(ctypes.byref(desc), x2d.data_ptr(), x2d.stride(0), y2d.data_ptr(),
                                         y2d.stride(0), tokens, ws.data_ptr(), ws.numel(), flags, _stream(dev))
     check(rc, "vptq_b200_quant_gemv")
@@ -331,8 +357,8 @@ def tp_untag(tagged: torch.Tensor, y: torch.Tensor, exchange: TpExchange) -> Non
 def quant_gemm(desc: LinearDesc, x2d: torch.Tensor, y2d: torch.Tensor, flags: int = 0) -> None:
     dev = x2d.device
     tokens = x2d.shape[0]
-    with torch.cuda.device(dev):
-        ws = workspace(dev, workspace_bytes(desc, tokens, OP_GEMM))
+    with _on_device(dev):
+        ws = workspace(dev, _ws_bytes_cached(desc, tokens, OP_GEMM))
         rc = lib().vptq_b200_quant_gemm(ctypes.byref(desc), x2d.data_ptr(), x2d.stride(0), y2d.data_ptr(),
                                         y2d.stride(0), tokens, ws.data_ptr(), ws.numel(), flags, _stream(dev))
     check(rc, "vptq_b200_quant_gemm")
