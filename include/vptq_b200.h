@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define VPTQ_B200_ABI_VERSION 5
+#define VPTQ_B200_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define VPTQ_B200_API __attribute__((visibility("default")))
@@ -186,6 +186,18 @@ VPTQ_B200_API int vptq_b200_lists_build_host(const int32_t* indices_host, int64_
                                              int32_t num_res_centroids, const uint16_t* perm_host,
                                              void* stream_out, size_t stream_capacity, uint32_t* tab_out,
                                              size_t* steps_out, int32_t* tile_cols_out);
+
+/*
+ * Optional second load-time pass over built lists (HOST memory, in place; CPU threads, 0 = all cores):
+ * re-orders the entries INSIDE every list -- the kernel's result does not depend on that order, its
+ * shared-memory bank conflicts do.  Per 32-entry step the entries are chosen so that each quarter-warp
+ * reads 8 different 16-byte codebook bank groups (index & 7) and, as far as a bipartite matching
+ * allows, the 32 lanes read 32 different x' banks ((column >> 1) & 31).  vptq_b200.lists.build_lists
+ * applies it by default (VPTQ_B200_LISTS_DEAL=0 skips it); a host using vptq_b200_lists_build_host
+ * calls it on (stream_out, tab_out) before uploading.  units = number of lists (tab has units + 1 words).
+ */
+VPTQ_B200_API int vptq_b200_lists_deal_host(uint32_t* stream_host, const uint32_t* tab_host, int64_t units,
+                                            int32_t threads);
 
 /*
  * Decode path, horizontally fused: up to 4 layers that read the SAME x (q/k/v, gate/up of a

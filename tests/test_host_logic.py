@@ -140,7 +140,7 @@ def test_c_abi_exports_every_declared_symbol():
     from vptq_b200 import native
     L = native.lib()
     syms = _header_symbols()
-    assert len(syms) == 14 and sorted(native.EXPORTS) == syms
+    assert len(syms) == 15 and sorted(native.EXPORTS) == syms
     for s in syms:
         assert hasattr(L, s), s
     assert L.vptq_b200_abi_version() == native.ABI_VERSION

@@ -4,6 +4,7 @@ CPU only: the builder is checked against the oracle through a float64 evaluation
 the C host builder (byte-identical), and the kernel's work partition (csrc/gemv_lists.cu: CTA unit ranges,
 warp runs, stage sequence, piece merge, row-block arrival counts) is mirrored in integers."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -21,9 +22,16 @@ CASES = [
 ]
 
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _layer(c, dtype="fp16", perm=True):
+    return vo.make_layer(c["I"], c["O"], vector_len=8, num_centroids=c["K"], num_res_centroids=c["Kr"], dtype=dtype,
+                         seed=11, enable_perm=perm)
+
+
 def _build(c, dtype="fp16", perm=True):
-    L = vo.make_layer(c["I"], c["O"], vector_len=8, num_centroids=c["K"], num_res_centroids=c["Kr"], dtype=dtype,
-                      seed=11, enable_perm=perm)
+    L = _layer(c, dtype, perm)
     ind = torch.from_numpy(np.ascontiguousarray(L.indices))
     pt = None if L.perm is None else torch.from_numpy(np.asarray(L.perm).astype(np.uint16).astype(np.int64))
     stream, tab, tcw = lists.build_lists(ind, num_centroids=c["K"], num_res_centroids=c["Kr"], in_features=c["I"],
@@ -232,7 +240,7 @@ def test_kernel_partition_random_list_lengths(seed):
 # ------------------------------------------------------------------------------------------------------
 # C host builder
 # ------------------------------------------------------------------------------------------------------
-def _c_build(L, c, perm=True):
+def _c_build(L, c, perm=True, deal=True):
     from vptq_b200 import native
     lib = native.lib()
     ind = np.ascontiguousarray(L.indices[0])
@@ -248,6 +256,8 @@ def _c_build(L, c, perm=True):
     rc = lib.vptq_b200_lists_build_host(*args, out.ctypes.data, out.nbytes, tab_c.ctypes.data, ctypes.byref(steps),
                                         ctypes.byref(tcw))
     assert rc == 0, native.last_error()
+    if deal:   # the second load-time pass lists.build_lists applies by default
+        assert lib.vptq_b200_lists_deal_host(out.ctypes.data, tab_c.ctypes.data, len(tab_c) - 1, 0) == 0, native.last_error()
     return out, tab_c, steps.value, tcw.value, (args, ind, pp)   # (ind / pp keep the host buffers alive)
 
 
@@ -286,6 +296,55 @@ def test_builders_agree_on_random_shapes():
         y = _eval(L, c, stream, tab, x)
         y_star = vo.quant_gemm(x, L).astype(np.float64).reshape(-1)
         assert np.max(np.abs(y - y_star)) <= 1e-5 * max(1.0, np.max(np.abs(y_star))), c
+
+
+def _list_bounds(tab):
+    t = tab.astype(np.int64) & 0xFFFFFFFF
+    first, end, tail = t[:-1] & lists.STEP_MASK, t[1:] & lists.STEP_MASK, t[:-1] >> 26
+    return first * 32, (end - 1) * 32 + tail, end * 32      # entry range [a, b) of every list, c = end of its padding
+
+
+@pytest.mark.parametrize("c", CASES)
+def test_dealing_only_reorders_inside_lists(c):
+    """vptq_b200_lists_deal_host: every list keeps its multiset of entries, padding stays zero, the result does not
+    depend on the number of threads, and running it again on its own output changes nothing a sum could see."""
+    from vptq_b200 import native
+    L = _layer(c)
+    pt = None if L.perm is None else torch.from_numpy(np.asarray(L.perm).astype(np.uint16).astype(np.int64))
+    kw = dict(num_centroids=c["K"], num_res_centroids=c["Kr"], in_features=c["I"], out_features=c["O"], perm=pt)
+    ind = torch.from_numpy(np.ascontiguousarray(L.indices))
+    raw, tab, _ = lists.build_lists(ind, deal=False, **kw)
+    dealt, tab2, _ = lists.build_lists(ind, deal=True, **kw)
+    assert torch.equal(tab, tab2)
+    r, d = raw.numpy().reshape(-1).view(np.uint32), dealt.numpy().reshape(-1).view(np.uint32)
+    a, b, e = _list_bounds(tab.numpy())
+    for u in range(len(a)):
+        assert np.array_equal(np.sort(r[a[u]:b[u]]), np.sort(d[a[u]:b[u]])), u
+        assert not d[b[u]:e[u]].any(), u
+    one = raw.clone()
+    th = tab.contiguous()
+    assert native.lib().vptq_b200_lists_deal_host(one.data_ptr(), th.data_ptr(), th.numel() - 1, 1) == 0
+    assert torch.equal(one, dealt)
+
+
+def test_dealing_lowers_the_modelled_bank_conflicts():
+    """On a K = 65536 layer with random indices the re-ordering must not make either gather worse, and must cut the
+    x' gather's conflicts (the model of tools/deal_stats.py: distinct addresses per bank group / bank)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("deal_stats", os.path.join(ROOT, "tools", "deal_stats.py"))
+    ds = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ds)
+    c = dict(K=65536, Kr=256, I=4096, O=128)
+    L = _layer(c)
+    pt = torch.from_numpy(np.asarray(L.perm).astype(np.uint16).astype(np.int64))
+    kw = dict(num_centroids=c["K"], num_res_centroids=c["Kr"], in_features=c["I"], out_features=c["O"], perm=pt)
+    ind = torch.from_numpy(np.ascontiguousarray(L.indices))
+    raw, tab, _ = lists.build_lists(ind, deal=False, **kw)
+    dealt, _, _ = lists.build_lists(ind, deal=True, **kw)
+    tb = tab.numpy().astype(np.int64) & 0xFFFFFFFF
+    c0, x0 = ds.wavefronts(raw.numpy().view(np.uint32), tb)
+    c1, x1 = ds.wavefronts(dealt.numpy().view(np.uint32), tb)
+    assert c1 <= c0 + 1e-9 and x1 < x0 - 0.5, (c0, x0, c1, x1)
 
 
 def test_host_builder_rejects_what_the_kernel_does_not_cover():

@@ -1,7 +1,10 @@
 // Host-side (CPU) builder of the slice x tile lists: the C-ABI counterpart of vptq_b200/lists.py for
 // hosts that are not python.  Pure data layout, no GPU work; format contract in include/vptq_b200.h
 // (vptq_linear_desc::lists_stream / lists_tab), consumer gemv_lists.cu.
+#include <algorithm>
+#include <atomic>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -20,10 +23,170 @@ inline uint32_t field_at(const uint32_t* row, int64_t words, int64_t j, int b) {
   return b >= 32 ? uint32_t(v) : uint32_t(v & ((uint64_t(1) << b) - 1));
 }
 
+// -------------------------------------------------------------------------------------------------------------
+// Bank-aware ordering of ONE list (a pure re-ordering of its entries: the sum the decode kernel forms does not
+// depend on it, its speed does).  In the kernel the 32 lanes of a warp take the 32 entries of a step; two gathers
+// pay for shared-memory bank conflicts (profiles/r02_ncu_shapes_metrics.csv: 3.8 of 14.3 load wavefronts per step):
+//   * the 128-bit codebook gather is conflict-free inside a quarter-warp when its 8 lanes read 8 different 16-byte
+//     bank groups, i.e. hold 8 different classes (index & 7);
+//   * the 16-bit x' gather is conflict-free when the 32 lanes read 32 different 4-byte banks, bank = (column >> 1) & 31.
+// Per step: every class gets up to 4 slots (one per quarter; the class's entries are spread over the remaining steps),
+// the slots are matched to distinct x' banks by augmenting paths (a 32 x 32 bipartite matching), unmatched slots take
+// their class's fullest bank, spare lanes take entries of the fullest classes (unused banks first).  Deterministic and
+// sequential; on random indices the two gathers drop from 8.6 to 7.5 wavefronts per step (the intrinsic imbalance
+// of ~256 entries over 32 banks / 8 groups keeps the floor near 6.5).
+// -------------------------------------------------------------------------------------------------------------
+constexpr int kDealMaxEntries = 4096;
+
+inline int ctz32(uint32_t v) { return __builtin_ctz(v); }
+
+void deal_list(uint32_t* entries, int n, std::vector<uint32_t>& sorted) {
+  if (n < 2 || n > kDealMaxEntries) return;
+  const int S = (n + kStep - 1) / kStep;
+  // stable counting sort by key = class * 32 + bank
+  int start[257] = {0}, cur[256];
+  auto key = [](uint32_t e) { return int((e & 7u) << 5 | ((e >> 13) & 31u)); };
+  for (int i = 0; i < n; ++i) ++start[key(entries[i]) + 1];
+  for (int k = 0; k < 256; ++k) start[k + 1] += start[k];
+  for (int k = 0; k < 256; ++k) cur[k] = start[k];
+  sorted.resize(size_t(n));
+  for (int i = 0; i < n; ++i) sorted[size_t(cur[key(entries[i])]++)] = entries[i];
+  for (int k = 0; k < 256; ++k) cur[k] = start[k];  // pop cursor: front of every bucket
+  int cnt[8];
+  uint32_t avail[8];
+  for (int g = 0; g < 8; ++g) {
+    cnt[g] = start[g * 32 + 32] - start[g * 32], avail[g] = 0u;
+    for (int b = 0; b < 32; ++b)
+      if (start[g * 32 + b + 1] > start[g * 32 + b]) avail[g] |= 1u << b;
+  }
+  auto pop = [&](int g, int b) {
+    const int k = g * 32 + b;
+    const uint32_t e = sorted[size_t(cur[k]++)];
+    if (cur[k] == start[k + 1]) avail[g] &= ~(1u << b);
+    --cnt[g];
+    return e;
+  };
+  auto fullest_bank = [&](int g) {
+    int best = -1, bc = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int c = start[g * 32 + b + 1] - cur[g * 32 + b];
+      if (c > bc) best = b, bc = c;
+    }
+    return best;
+  };
+  int pos = 0;
+  for (int s = 0; s < S; ++s) {
+    const int rem = S - s, cap = s < S - 1 ? kStep : n - kStep * (S - 1);
+    int want[8], tot = 0;
+    for (int g = 0; g < 8; ++g) want[g] = std::min(4, (cnt[g] + rem - 1) / rem), tot += want[g];
+    for (int g = 7; tot > cap; g = (g + 7) & 7)
+      if (want[g] > 0) --want[g], --tot;
+    int slots[32], nslots = 0;
+    for (int q = 0; q < 4; ++q)
+      for (int g = 0; g < 8; ++g)
+        if (want[g] > q) slots[nslots++] = g;
+    // maximum matching slots -> distinct banks (iterative augmenting paths)
+    int match_bank[32], slot_bank[32], parent[32];
+    for (int b = 0; b < 32; ++b) match_bank[b] = -1;
+    for (int i = 0; i < nslots; ++i) slot_bank[i] = -1;
+    for (int si = 0; si < nslots; ++si) {
+      uint32_t visited = 0u, mask[33];
+      int stack[33], top = 0, found = -1;
+      stack[0] = si, mask[0] = avail[slots[si]];
+      while (top >= 0) {
+        const uint32_t m = mask[top] & ~visited;
+        if (!m) {
+          --top;
+          continue;
+        }
+        const int b = ctz32(m);
+        visited |= 1u << b;
+        mask[top] = m & ~(1u << b);
+        parent[b] = stack[top];
+        if (match_bank[b] < 0) {
+          found = b;
+          break;
+        }
+        const int nxt = match_bank[b];
+        ++top;
+        stack[top] = nxt, mask[top] = avail[slots[nxt]];
+      }
+      for (int b = found; b >= 0;) {  // flip the path
+        const int c = parent[b], prev = slot_bank[c];
+        match_bank[b] = c, slot_bank[c] = b;
+        if (c == si) break;
+        b = prev;
+      }
+    }
+    uint32_t lanes[32];
+    bool taken[32] = {false};
+    int usedq[8] = {0};
+    uint32_t usedb = 0u;
+    // the quarter a class's k-th slot lands in is fixed by slot order; matched slots pop first (an unmatched slot
+    // of the same class must not take the entry a matched one was promised)
+    int lane_of[32];
+    for (int i = 0; i < nslots; ++i) lane_of[i] = (usedq[slots[i]]++) * 8 + slots[i];
+    for (int pass = 0; pass < 2; ++pass)
+      for (int i = 0; i < nslots; ++i) {
+        if ((slot_bank[i] >= 0) != (pass == 0)) continue;
+        const int g = slots[i], b = slot_bank[i] >= 0 ? slot_bank[i] : fullest_bank(g);
+        lanes[lane_of[i]] = pop(g, b), taken[lane_of[i]] = true;
+        usedb |= 1u << b;
+      }
+    int placed = nslots;
+    for (int lane = 0; lane < kStep && placed < cap; ++lane) {
+      if (taken[lane]) continue;
+      int g = 0;
+      for (int c = 1; c < 8; ++c)
+        if (cnt[c] > cnt[g]) g = c;
+      if (cnt[g] == 0) break;
+      const uint32_t fresh = avail[g] & ~usedb;
+      const int b = ctz32(fresh ? fresh : avail[g]);
+      lanes[lane] = pop(g, b), taken[lane] = true;
+      usedb |= 1u << b;
+      ++placed;
+    }
+    // a step's valid entries form a prefix (only the last step can be partial)
+    for (int lane = 0; lane < kStep; ++lane)
+      if (taken[lane]) entries[pos++] = lanes[lane];
+  }
+}
+
 }  // namespace
 }  // namespace vptq_b200
 
 using namespace vptq_b200;
+
+extern "C" int vptq_b200_lists_deal_host(uint32_t* stream_host, const uint32_t* tab_host, int64_t units, int32_t threads) {
+  if (!stream_host || !tab_host || units < 0) {
+    set_error("lists_deal_host: NULL argument");
+    return VPTQ_ERR_INVALID;
+  }
+  int nt = threads > 0 ? threads : int(std::thread::hardware_concurrency());
+  nt = std::max(1, std::min<int>(nt, int(std::min<int64_t>(units / 64 + 1, 256))));
+  std::atomic<int64_t> next{0};
+  auto work = [&]() {
+    std::vector<uint32_t> scratch;
+    for (;;) {
+      const int64_t u0 = next.fetch_add(256);
+      if (u0 >= units) break;
+      for (int64_t u = u0; u < std::min<int64_t>(units, u0 + 256); ++u) {
+        const uint32_t first = tab_host[u] & 0x3ffffffu, end = tab_host[u + 1] & 0x3ffffffu, tail = tab_host[u] >> 26;
+        if (end <= first) continue;
+        const int n = int(end - first - 1) * kStep + int(tail);
+        deal_list(stream_host + size_t(first) * kStep, n, scratch);
+      }
+    }
+  };
+  if (nt == 1) {
+    work();
+  } else {
+    std::vector<std::thread> pool;
+    for (int i = 0; i < nt; ++i) pool.emplace_back(work);
+    for (auto& t : pool) t.join();
+  }
+  return 0;
+}
 
 extern "C" int vptq_b200_lists_build_host(const int32_t* indices_host, int64_t index_stride_row, int32_t out_features,
                                           int32_t in_features, int32_t num_centroids, int32_t num_res_centroids,

@@ -17,7 +17,9 @@ A sum does not care about the order of its terms, so the fields of every index r
     fall into that (tile, slice).  Entry = 32 bits: index & 4095 | column << 12 | residual index << 24
     -- 4 bytes per field instead of the 3 packed + 5 listed bytes of the round-1 format;
   * inside a list the entries are dealt round-robin over the eight 16-byte bank groups (index & 7), so the
-    8 lanes of a quarter-warp read 8 different bank groups of the slice: conflict-free LDS.128;
+    8 lanes of a quarter-warp read 8 different bank groups of the slice: conflict-free LDS.128; a second pass
+    (`deal_lists`, C code in the shared library, CPU threads) re-orders every list so that the 32 lanes of a
+    step also read distinct x' banks where a matching exists -- pure re-ordering, results unchanged;
   * lists are padded to whole steps of 32 entries (every list has >= 1 step); the padding words are 0 and
     the kernel masks them with the list's tail count, so no null column is needed.
 
@@ -29,6 +31,8 @@ host-side data layout, not a compute path: the kernel does all arithmetic.
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -58,9 +62,30 @@ def eligible(*, vector_len: int, num_centroids: int, num_res_centroids: int, num
             and 8 <= in_features <= 65535)
 
 
+DEAL_DEFAULT = "1"   # VPTQ_B200_LISTS_DEAL when unset
+
+
+def deal_lists(stream: torch.Tensor, tab: torch.Tensor, threads: int = 0) -> torch.Tensor:
+    """Bank-aware re-ordering of the entries inside every list (vptq_b200_lists_deal_host, include/vptq_b200.h).
+
+    Runs on the host (C code, `threads` CPU threads, 0 = all): a device `stream` makes the round trip through
+    host memory once, at load time.  Returns `stream` (re-ordered in place)."""
+    from . import native
+    host = stream.detach().to("cpu").contiguous()
+    tab_h = tab.detach().to("cpu").contiguous()
+    native.check(native.lib().vptq_b200_lists_deal_host(ctypes.c_void_p(host.data_ptr()), ctypes.c_void_p(tab_h.data_ptr()),
+                                                        tab_h.numel() - 1, int(threads)), "lists_deal_host")
+    if host.data_ptr() != stream.data_ptr():
+        stream.copy_(host)
+    return stream
+
+
 def build_lists(indices: torch.Tensor, *, num_centroids: int, num_res_centroids: int, in_features: int,
-                out_features: int, perm: Optional[torch.Tensor]) -> Tuple[torch.Tensor, torch.Tensor, int]:
-    """packed int32 [1, >=Ro, W] (+ perm [I], uint16 payload) -> (stream int32 [T, 32], tab int32 [U+1], TCW)."""
+                out_features: int, perm: Optional[torch.Tensor], deal: Optional[bool] = None
+                ) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """packed int32 [1, >=Ro, W] (+ perm [I], uint16 payload) -> (stream int32 [T, 32], tab int32 [U+1], TCW).
+
+    deal: run `deal_lists` on the result (None = VPTQ_B200_LISTS_DEAL, default on)."""
     K, Kr, I = int(num_centroids), int(num_res_centroids), int(in_features)
     Ro = (int(out_features) + 7) // 8
     ib = K.bit_length() - 1
@@ -113,7 +138,12 @@ def build_lists(indices: torch.Tensor, *, num_centroids: int, num_res_centroids:
     tab = first.clone()
     tab[:-1] |= tail_rc.t().contiguous().view(-1) << 26
     tab = torch.where(tab >= (1 << 31), tab - (1 << 32), tab).to(torch.int32)
-    return words.view(T, STEP).contiguous(), tab.contiguous(), TCW
+    stream, tab = words.view(T, STEP).contiguous(), tab.contiguous()
+    if deal is None:
+        deal = os.environ.get("VPTQ_B200_LISTS_DEAL", DEAL_DEFAULT) not in ("0", "off", "")
+    if deal:
+        deal_lists(stream, tab)
+    return stream, tab, TCW
 
 
 def emulate(stream: torch.Tensor, tab: torch.Tensor, *, num_centroids: int, num_res_centroids: int,

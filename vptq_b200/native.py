@@ -23,14 +23,14 @@ VPTQ_FP16, VPTQ_BF16 = 0, 1
 OP_GEMV, OP_DEQUANT, OP_GEMM, OP_GEMV_V2 = 0, 1, 2, 3
 FLAG_PDL = 1
 TP_PLAIN, TP_TAGGED = 0, 1
-ABI_VERSION = 5
+ABI_VERSION = 6
 LISTS_DEFAULT = "1"   # VPTQ_B200_LISTS when unset
 
 EXPORTS = (
     "vptq_b200_abi_version", "vptq_b200_last_error", "vptq_b200_workspace_bytes", "vptq_b200_quant_gemv",
     "vptq_b200_dequant", "vptq_b200_quant_gemm", "vptq_b200_quant_gemv_v2", "vptq_b200_linear_host",
     "vptq_b200_debug_phase_stamps", "vptq_b200_quant_gemv_multi", "vptq_b200_quant_gemv_multi_tp",
-    "vptq_b200_lists_build_host", "vptq_b200_quant_gemv_multi_ws", "vptq_b200_tp_untag",
+    "vptq_b200_lists_build_host", "vptq_b200_quant_gemv_multi_ws", "vptq_b200_tp_untag", "vptq_b200_lists_deal_host",
 )
 
 MAX_FUSED, MAX_RANKS = 4, 8
@@ -109,6 +109,8 @@ def lib() -> ctypes.CDLL:
         L.vptq_b200_lists_build_host.argtypes = [vp, i64, i32, i32, i32, i32, vp, vp, sz, vp, ctypes.POINTER(sz),
                                                  ctypes.POINTER(i32)]
         L.vptq_b200_lists_build_host.restype = ctypes.c_int
+        L.vptq_b200_lists_deal_host.argtypes = [vp, vp, i64, i32]
+        L.vptq_b200_lists_deal_host.restype = ctypes.c_int
         L.vptq_b200_tp_untag.argtypes = [vp, vp, i32, ctypes.POINTER(TpExchange), vp]
         L.vptq_b200_tp_untag.restype = ctypes.c_int
         L.vptq_b200_debug_phase_stamps.argtypes = [vp]
