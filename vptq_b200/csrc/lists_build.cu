@@ -37,6 +37,10 @@ inline uint32_t field_at(const uint32_t* row, int64_t words, int64_t j, int b) {
 // of ~256 entries over 32 banks / 8 groups keeps the floor near 6.5).
 // -------------------------------------------------------------------------------------------------------------
 constexpr int kDealMaxEntries = 4096;
+#ifndef VPTQ_DEAL_BIAS
+#define VPTQ_DEAL_BIAS 0.5f
+#endif
+constexpr float kDealBias = VPTQ_DEAL_BIAS;
 
 inline int ctz32(uint32_t v) { return __builtin_ctz(v); }
 
@@ -52,100 +56,143 @@ void deal_list(uint32_t* entries, int n, std::vector<uint32_t>& sorted) {
   sorted.resize(size_t(n));
   for (int i = 0; i < n; ++i) sorted[size_t(cur[key(entries[i])]++)] = entries[i];
   for (int k = 0; k < 256; ++k) cur[k] = start[k];  // pop cursor: front of every bucket
-  int cnt[8];
-  uint32_t avail[8];
+  int cnt[8], nb[32] = {0};
+  int left[8][32];                                  // entries still in bucket (class, bank)
   for (int g = 0; g < 8; ++g) {
-    cnt[g] = start[g * 32 + 32] - start[g * 32], avail[g] = 0u;
-    for (int b = 0; b < 32; ++b)
-      if (start[g * 32 + b + 1] > start[g * 32 + b]) avail[g] |= 1u << b;
+    cnt[g] = 0;
+    for (int b = 0; b < 32; ++b) left[g][b] = start[g * 32 + b + 1] - start[g * 32 + b], cnt[g] += left[g][b], nb[b] += left[g][b];
   }
-  auto pop = [&](int g, int b) {
-    const int k = g * 32 + b;
-    const uint32_t e = sorted[size_t(cur[k]++)];
-    if (cur[k] == start[k + 1]) avail[g] &= ~(1u << b);
-    --cnt[g];
-    return e;
-  };
-  auto fullest_bank = [&](int g) {
-    int best = -1, bc = 0;
-    for (int b = 0; b < 32; ++b) {
-      const int c = start[g * 32 + b + 1] - cur[g * 32 + b];
-      if (c > bc) best = b, bc = c;
-    }
-    return best;
-  };
   int pos = 0;
   for (int s = 0; s < S; ++s) {
     const int rem = S - s, cap = s < S - 1 ? kStep : n - kStep * (S - 1);
+    // how many lanes every class gets.  A quarter-warp costs one wavefront when its 8 lanes hold 8 different
+    // classes and two when some class appears twice -- no matter how many do.  So the unavoidable doublings (the
+    // classes are never equally full) are paid for in as few quarters as possible: a step is either all-distinct
+    // (4 lanes per class) or carries `dq` "double quarters", in each of which up to 4 short classes leave a hole
+    // and as many long classes appear twice.
     int want[8], tot = 0;
-    for (int g = 0; g < 8; ++g) want[g] = std::min(4, (cnt[g] + rem - 1) / rem), tot += want[g];
-    for (int g = 7; tot > cap; g = (g + 7) & 7)
-      if (want[g] > 0) --want[g], --tot;
-    int slots[32], nslots = 0;
-    for (int q = 0; q < 4; ++q)
+    if (s == S - 1) {
+      for (int g = 0; g < 8; ++g) want[g] = cnt[g], tot += cnt[g];   // everything that is left (= cap)
+    } else {
+      int n_rem = 0;
+      for (int g = 0; g < 8; ++g) n_rem += cnt[g];
+      float E[8], D = 0.f, emax = 0.f;
+      for (int g = 0; g < 8; ++g) {
+        E[g] = float(cnt[g]) - float(n_rem) * 0.125f;
+        if (E[g] > 0.f) D += E[g], emax = std::max(emax, E[g]);
+      }
+      const float DQ = std::max(D * 0.25f, emax);
+      const int dq = std::min(4, std::max(0, int(std::ceil(DQ / float(rem) - kDealBias))));
+      for (int g = 0; g < 8; ++g) want[g] = 4;
+      for (int q = 0; q < dq; ++q) {
+        int lo[8], hi[8];
+        for (int g = 0; g < 8; ++g) lo[g] = hi[g] = g;
+        std::stable_sort(lo, lo + 8, [&](int x, int y) { return E[x] < E[y]; });
+        std::stable_sort(hi, hi + 8, [&](int x, int y) { return E[x] > E[y]; });
+        int h = 0;
+        while (h < 4 && E[lo[h]] <= -0.5f && want[lo[h]] > 0 && E[hi[h]] > 0.f && cnt[hi[h]] > want[hi[h]]) ++h;
+        for (int i = 0; i < h; ++i) --want[lo[i]], E[lo[i]] += 1.f, ++want[hi[i]], E[hi[i]] -= 1.f;
+      }
+      for (int g = 0; g < 8; ++g) want[g] = std::min(want[g], cnt[g]), tot += want[g];
+      while (tot < cap) {   // a class ran dry: its lanes go to the classes with the most entries left
+        int g = 0;
+        for (int c = 1; c < 8; ++c)
+          if (cnt[c] - want[c] > cnt[g] - want[g]) g = c;
+        ++want[g], ++tot;
+      }
+    }
+    // route the class lanes to banks: a flow classes -> buckets -> banks on 8 + 32 nodes.  Banks are served in
+    // order of the entries they still hold, each up to ITS share of the remaining steps (so a heavy bank doubles
+    // up early, together with the other heavy ones, instead of piling up in the last steps); what is still
+    // unrouted after that raises every bank by one more, heaviest first.
+    int f[8][32] = {{0}}, supply[8], used[32] = {0}, unrouted = tot;
+    uint32_t resid[8];   // banks a class can still send one more entry to
+    uint8_t has[32];     // classes currently routed into a bank
+    for (int g = 0; g < 8; ++g) {
+      supply[g] = want[g], resid[g] = 0u;
+      for (int b = 0; b < 32; ++b)
+        if (left[g][b] > 0) resid[g] |= 1u << b;
+    }
+    for (int b = 0; b < 32; ++b) has[b] = 0;
+    auto augment = [&](int t) {
+      int parent_b[32], parent_c[8], queue[8], qh = 0, qt = 0;
+      uint32_t vis_b = 0u, vis_c = 0u;
       for (int g = 0; g < 8; ++g)
-        if (want[g] > q) slots[nslots++] = g;
-    // maximum matching slots -> distinct banks (iterative augmenting paths)
-    int match_bank[32], slot_bank[32], parent[32];
-    for (int b = 0; b < 32; ++b) match_bank[b] = -1;
-    for (int i = 0; i < nslots; ++i) slot_bank[i] = -1;
-    for (int si = 0; si < nslots; ++si) {
-      uint32_t visited = 0u, mask[33];
-      int stack[33], top = 0, found = -1;
-      stack[0] = si, mask[0] = avail[slots[si]];
-      while (top >= 0) {
-        const uint32_t m = mask[top] & ~visited;
-        if (!m) {
-          --top;
-          continue;
-        }
-        const int b = ctz32(m);
-        visited |= 1u << b;
-        mask[top] = m & ~(1u << b);
-        parent[b] = stack[top];
-        if (match_bank[b] < 0) {
-          found = b;
+        if (supply[g] > 0) vis_c |= 1u << g, parent_c[g] = -1, queue[qt++] = g;
+      bool found = false;
+      while (qh < qt && !found) {
+        const int g = queue[qh++];
+        uint32_t m = resid[g] & ~vis_b;
+        if (m >> t & 1u) {
+          parent_b[t] = g, found = true;
           break;
         }
-        const int nxt = match_bank[b];
-        ++top;
-        stack[top] = nxt, mask[top] = avail[slots[nxt]];
+        for (; m; m &= m - 1) {
+          const int b = ctz32(m);
+          vis_b |= 1u << b, parent_b[b] = g;
+          for (uint32_t cm = has[b] & ~vis_c; cm; cm &= cm - 1) {
+            const int c = ctz32(cm);
+            vis_c |= 1u << c, parent_c[c] = b, queue[qt++] = c;
+          }
+        }
       }
-      for (int b = found; b >= 0;) {  // flip the path
-        const int c = parent[b], prev = slot_bank[c];
-        match_bank[b] = c, slot_bank[c] = b;
-        if (c == si) break;
-        b = prev;
+      if (!found) return false;
+      for (int b = t;;) {
+        const int g = parent_b[b];
+        if (++f[g][b] == left[g][b]) resid[g] &= ~(1u << b);
+        has[b] |= uint8_t(1u << g);
+        const int pb = parent_c[g];
+        if (pb < 0) {
+          --supply[g];
+          break;
+        }
+        if (--f[g][pb] == 0) has[pb] &= uint8_t(~(1u << g));
+        resid[g] |= 1u << pb;
+        b = pb;
       }
+      ++used[t], --unrouted;
+      return true;
+    };
+    int order[32];
+    for (int b = 0; b < 32; ++b) order[b] = b;
+    std::stable_sort(order, order + 32, [&](int x, int y) { return nb[x] > nb[y]; });
+    for (int i = 0; i < 32 && unrouted > 0; ++i) {
+      const int b = order[i], need = (nb[b] + rem - 1) / rem;
+      for (int k = 0; k < need && unrouted > 0; ++k)
+        if (!augment(b)) break;
     }
+    while (unrouted > 0) {
+      bool progress = false;
+      for (int i = 0; i < 32 && unrouted > 0; ++i)
+        if (nb[order[i]] > used[order[i]] && augment(order[i])) progress = true;
+      if (!progress) break;  // cannot happen: a class with unrouted lanes has an unreserved entry in some bank
+    }
+    // lanes: a class's k-th entry goes to quarter k (lane 8 k + class) while k < 4; the extras fill the lanes the
+    // short classes left free, from the top, so that the doubled classes share the last quarter(s)
     uint32_t lanes[32];
     bool taken[32] = {false};
-    int usedq[8] = {0};
-    uint32_t usedb = 0u;
-    // the quarter a class's k-th slot lands in is fixed by slot order; matched slots pop first (an unmatched slot
-    // of the same class must not take the entry a matched one was promised)
-    int lane_of[32];
-    for (int i = 0; i < nslots; ++i) lane_of[i] = (usedq[slots[i]]++) * 8 + slots[i];
-    for (int pass = 0; pass < 2; ++pass)
-      for (int i = 0; i < nslots; ++i) {
-        if ((slot_bank[i] >= 0) != (pass == 0)) continue;
-        const int g = slots[i], b = slot_bank[i] >= 0 ? slot_bank[i] : fullest_bank(g);
-        lanes[lane_of[i]] = pop(g, b), taken[lane_of[i]] = true;
-        usedb |= 1u << b;
-      }
-    int placed = nslots;
-    for (int lane = 0; lane < kStep && placed < cap; ++lane) {
-      if (taken[lane]) continue;
-      int g = 0;
-      for (int c = 1; c < 8; ++c)
-        if (cnt[c] > cnt[g]) g = c;
-      if (cnt[g] == 0) break;
-      const uint32_t fresh = avail[g] & ~usedb;
-      const int b = ctz32(fresh ? fresh : avail[g]);
-      lanes[lane] = pop(g, b), taken[lane] = true;
-      usedb |= 1u << b;
-      ++placed;
+    uint32_t extras[32][8];   // [k - 4][class]: a class's 5th, 6th, ... entry
+    int kmax = 0;
+    bool extra_set[32][8] = {{false}};
+    for (int g = 0; g < 8; ++g) {
+      int k = 0;
+      for (int b = 0; b < 32; ++b)
+        for (int j = 0; j < f[g][b]; ++j) {
+          const uint32_t e = sorted[size_t(cur[g * 32 + b]++)];
+          if (k < 4) lanes[k * 8 + g] = e, taken[k * 8 + g] = true;
+          else extras[k - 4][g] = e, extra_set[k - 4][g] = true, kmax = std::max(kmax, k - 3);
+          ++k;
+        }
+      for (int b = 0; b < 32; ++b) left[g][b] -= f[g][b], cnt[g] -= f[g][b], nb[b] -= f[g][b];
     }
+    int lane = kStep - 1;
+    for (int k = 0; k < kmax; ++k)       // all 5th entries first, then the 6th ...: one class's extras land in
+      for (int g = 0; g < 8; ++g) {      // different quarters as long as the holes allow
+        if (!extra_set[k][g]) continue;
+        while (lane >= 0 && taken[lane]) --lane;
+        if (lane < 0) break;
+        lanes[lane] = extras[k][g], taken[lane] = true;
+      }
     // a step's valid entries form a prefix (only the last step can be partial)
     for (int lane = 0; lane < kStep; ++lane)
       if (taken[lane]) entries[pos++] = lanes[lane];
