@@ -327,6 +327,35 @@ def test_dealing_only_reorders_inside_lists(c):
     assert torch.equal(one, dealt)
 
 
+@pytest.mark.parametrize("kind", ["constant", "two_values", "one_slice", "long_lists"])
+def test_dealing_survives_degenerate_index_patterns(kind):
+    """All entries in one class, all in one slice, lists of 64 steps: still a permutation inside every list."""
+    from vptq_b200 import pack
+    g = torch.Generator().manual_seed(5)
+    K, Kr, I, O = 65536, 256, 1024, 40
+    Ro = O // 8
+    if kind == "constant":
+        idx = torch.full((1, Ro, I), 4099, dtype=torch.int64)
+    elif kind == "two_values":
+        idx = torch.where(torch.rand(1, Ro, I, generator=g) < 0.9, 8, 4097)
+    elif kind == "one_slice":    # 1024 entries in one list, the other 15 lists of the row empty
+        idx = torch.randint(0, 4096, (1, Ro, I), generator=g)
+    else:
+        K, I = 8192, 4096
+        idx = torch.randint(0, K, (1, Ro, I), generator=g)
+    ridx = torch.randint(0, Kr, idx.shape, generator=g)
+    packed = pack.pack_index(idx, K.bit_length() - 1, ridx, 8)
+    kw = dict(num_centroids=K, num_res_centroids=Kr, in_features=I, out_features=O, perm=None)
+    raw, tab, _ = lists.build_lists(packed, deal=False, **kw)
+    dealt, _, _ = lists.build_lists(packed, deal=True, **kw)
+    r, d = raw.numpy().reshape(-1).view(np.uint32), dealt.numpy().reshape(-1).view(np.uint32)
+    a, b, e = _list_bounds(tab.numpy())
+    assert int((b - a).sum()) == Ro * I
+    for u in range(len(a)):
+        assert np.array_equal(np.sort(r[a[u]:b[u]]), np.sort(d[a[u]:b[u]])), (kind, u)
+        assert not d[b[u]:e[u]].any(), (kind, u)
+
+
 def test_dealing_lowers_the_modelled_bank_conflicts():
     """On a K = 65536 layer with random indices the re-ordering must not make either gather worse, and must cut the
     x' gather's conflicts (the model of tools/deal_stats.py: distinct addresses per bank group / bank)."""
