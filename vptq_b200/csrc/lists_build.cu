@@ -41,6 +41,7 @@ constexpr int kDealMaxEntries = 4096;
 #define VPTQ_DEAL_BIAS 0.5f
 #endif
 constexpr float kDealBias = VPTQ_DEAL_BIAS;
+constexpr int64_t kDealChunk = 16;   // lists a worker thread takes at a time
 
 inline int ctz32(uint32_t v) { return __builtin_ctz(v); }
 
@@ -210,14 +211,14 @@ extern "C" int vptq_b200_lists_deal_host(uint32_t* stream_host, const uint32_t* 
     return VPTQ_ERR_INVALID;
   }
   int nt = threads > 0 ? threads : int(std::thread::hardware_concurrency());
-  nt = std::max(1, std::min<int>(nt, int(std::min<int64_t>(units / 64 + 1, 256))));
+  nt = std::max(1, std::min<int>(nt, int(std::min<int64_t>(units / kDealChunk + 1, 256))));
   std::atomic<int64_t> next{0};
   auto work = [&]() {
     std::vector<uint32_t> scratch;
     for (;;) {
-      const int64_t u0 = next.fetch_add(256);
+      const int64_t u0 = next.fetch_add(kDealChunk);
       if (u0 >= units) break;
-      for (int64_t u = u0; u < std::min<int64_t>(units, u0 + 256); ++u) {
+      for (int64_t u = u0; u < std::min<int64_t>(units, u0 + kDealChunk); ++u) {
         const uint32_t first = tab_host[u] & 0x3ffffffu, end = tab_host[u + 1] & 0x3ffffffu, tail = tab_host[u] >> 26;
         if (end <= first) continue;
         const int n = int(end - first - 1) * kStep + int(tail);
