@@ -9,10 +9,14 @@ usage: python tools/deal_stats.py [--O 4096] [--I 4096] [--K 65536] [--Kr 256] [
 import argparse
 import time
 
+import os
+import sys
+
 import numpy as np
 import torch
 
-from vptq_b200 import lists, pack
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from vptq_b200 import lists, pack  # noqa: E402
 
 
 def wavefronts(stream: np.ndarray, tab: np.ndarray):
