@@ -99,6 +99,7 @@ void deal_list(uint32_t* entries, int n, std::vector<uint32_t>& sorted) {
         int g = 0;
         for (int c = 1; c < 8; ++c)
           if (cnt[c] - want[c] > cnt[g] - want[g]) g = c;
+        if (cnt[g] <= want[g]) break;   // (cannot happen: a non-final step has >= 32 entries left)
         ++want[g], ++tot;
       }
     }
@@ -168,6 +169,7 @@ void deal_list(uint32_t* entries, int n, std::vector<uint32_t>& sorted) {
         if (nb[order[i]] > used[order[i]] && augment(order[i])) progress = true;
       if (!progress) break;  // cannot happen: a class with unrouted lanes has an unreserved entry in some bank
     }
+    if (unrouted > 0) break;     // (defensive) give up on this list: the check after the loop restores it
     // lanes: a class's k-th entry goes to quarter k (lane 8 k + class) while k < 4; the extras fill the lanes the
     // short classes left free, from the top, so that the doubled classes share the last quarter(s)
     uint32_t lanes[32];
@@ -198,6 +200,8 @@ void deal_list(uint32_t* entries, int n, std::vector<uint32_t>& sorted) {
     for (int lane = 0; lane < kStep; ++lane)
       if (taken[lane]) entries[pos++] = lanes[lane];
   }
+  // whatever happened above, the list must leave as a permutation of what came in
+  if (pos != n) std::copy(sorted.begin(), sorted.end(), entries);
 }
 
 }  // namespace
