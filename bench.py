@@ -608,10 +608,15 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": workload_string(m, q, cfg_name),
                        "parallelism": (f"tp{world} (out_features sharded; " +
-                                       ("exchange fused into the GEMV: NVLink peer stores + epoch flags, no NCCL call"
+                                       ("exchange fused into the GEMV: tagged 8-byte words stored into every peer over NVLink, "
+                                        "no fence / flag / NCCL call" if tp_mode == "p2p" else
+                                        "exchange fused into the GEMV: NVLink peer stores + epoch flags, no NCCL call"
                                         if tp_mode.startswith("p2p") else "1 NCCL all-reduce per launch: q|k|v, o, gate|up, down") + ")")
                                       if world > 1 else "single GPU",
                        "l2_policy": "inputs larger than L2: 2.6 GB of distinct packed indices streamed per step",
+                       "index_lists": ("slice x tile lists, entries re-ordered at load time for shared-memory banks "
+                                       "(vptq_b200_lists_deal_host)" if os.environ.get("VPTQ_B200_LISTS_DEAL", "1") not in ("0", "off", "")
+                                       else "slice x tile lists, round-robin order") if uses_lists else "none (generic kernel)",
                        "fusion": "q+k+v and gate+up each in one launch (vptq_b200_quant_gemv_multi)" if
                                  not os.environ.get("BENCH_NO_FUSE") else "one launch per linear",
                        "launch": ("one CUDA graph per token" if use_graph else "eager launches") +
