@@ -117,6 +117,15 @@ void deal_list(uint32_t* entries, int n, std::vector<uint32_t>& sorted) {
     }
     for (int b = 0; b < 32; ++b) has[b] = 0;
     auto augment = [&](int t) {
+      // the common case: a class that still has lanes to place holds an unreserved entry of bank t (the search
+      // below would return the same class: it pops the classes with lanes left first, in this order)
+      for (int g = 0; g < 8; ++g)
+        if (supply[g] > 0 && (resid[g] >> t & 1u)) {
+          if (++f[g][t] == left[g][t]) resid[g] &= ~(1u << t);
+          has[t] |= uint8_t(1u << g);
+          --supply[g], ++used[t], --unrouted;
+          return true;
+        }
       int parent_b[32], parent_c[8], queue[8], qh = 0, qt = 0;
       uint32_t vis_b = 0u, vis_c = 0u;
       for (int g = 0; g < 8; ++g)
